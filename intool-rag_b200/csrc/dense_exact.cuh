@@ -1,0 +1,377 @@
+// dense_exact.cuh — exact fp32 kernels of the flat index (CUDA cores).
+//
+//  * convert_pad / row_norms : `add` path (faiss IndexFlat::add, rag/storage/faiss_index.py:124)
+//  * exact_scan + exact_merge: exhaustive exact search under the total order (score best first,
+//    row asc).  This is the certified *fallback* of the tensor-core filter and HR_MODE_EXACT_SIMT.
+//  * rescore_finalize        : exact fp32 re-score of the filter's shortlist, final top-k, and the
+//    certificate that decides whether a query needs the fallback.
+//
+// "Exact score" has ONE definition, used by every kernel here (so fallback and re-score agree
+// bit for bit): lane l of a warp accumulates elements i with (i/4)%32 == l in increasing i with a
+// single fp32 fma chain, then a 16/8/4/2/1 xor-butterfly sums the 32 lanes.
+#pragma once
+#include "common.cuh"
+
+namespace hr {
+
+constexpr int kMetricIP = 0;
+constexpr int kMetricL2 = 1;
+
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float4 r;
+  r.x = __uint_as_float(u.x << 16);
+  r.y = __uint_as_float(u.x & 0xFFFF0000u);
+  r.z = __uint_as_float(u.y << 16);
+  r.w = __uint_as_float(u.y & 0xFFFF0000u);
+  return r;
+}
+
+// F queries (rows of q, stride q_stride floats) against one stored row; every lane gets the sums.
+template <typename T, int METRIC, int F>
+__device__ __forceinline__ void warp_exact_scores(const T* __restrict__ xrow, const float* q, int q_stride,
+                                                  int ld, int lane, float (&out)[F]) {
+  float acc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = 0.f;
+  for (int c = lane * 4; c < ld; c += 128) {
+    float4 xv = load4<T>(xrow + c);
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      float4 qv = *reinterpret_cast<const float4*>(q + (size_t)f * q_stride + c);
+      if (METRIC == kMetricIP) {
+        acc[f] = fmaf(xv.x, qv.x, acc[f]);
+        acc[f] = fmaf(xv.y, qv.y, acc[f]);
+        acc[f] = fmaf(xv.z, qv.z, acc[f]);
+        acc[f] = fmaf(xv.w, qv.w, acc[f]);
+      } else {
+        float d0 = xv.x - qv.x, d1 = xv.y - qv.y, d2 = xv.z - qv.z, d3 = xv.w - qv.w;
+        acc[f] = fmaf(d0, d0, acc[f]);
+        acc[f] = fmaf(d1, d1, acc[f]);
+        acc[f] = fmaf(d2, d2, acc[f]);
+        acc[f] = fmaf(d3, d3, acc[f]);
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < F; ++f) out[f] = warp_sum_xor(acc[f]);
+}
+
+// ---- add path ---------------------------------------------------------------------------------
+// src fp32 [n, d] -> dst T [n, ld] (zero padded), plus |x|^2 per row and the running max norm.
+template <typename T>
+__global__ void convert_pad_norm_kernel(const float* __restrict__ src, int64_t n, int d, T* __restrict__ dst,
+                                        int ld, float* __restrict__ norms, unsigned int* __restrict__ max_norm2_ord) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float* s = src + r * (int64_t)d;
+    T* o = dst + r * (int64_t)ld;
+    float acc = 0.f;
+    for (int c = lane; c < ld; c += 32) {
+      float v = (c < d) ? s[c] : 0.f;
+      T t = (T)v;
+      o[c] = t;
+      float back = (float)t;
+      acc = fmaf(back, back, acc);
+    }
+    acc = warp_sum_xor(acc);
+    if (lane == 0) {
+      norms[r] = acc;
+      atomicMax(max_norm2_ord, f2ord(acc));
+    }
+  }
+}
+
+// queries fp32 [nq, d] -> padded fp32 [nq, ld] (+ optional bf16 copy for the bf16 filter)
+__global__ void pad_queries_kernel(const float* __restrict__ q, int64_t nq, int d, int ld, float* __restrict__ qp,
+                                   __nv_bfloat16* __restrict__ qh) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = nq * (int64_t)ld;
+  for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / ld;
+    int c = (int)(i - r * ld);
+    float v = (c < d) ? q[r * (int64_t)d + c] : 0.f;
+    qp[i] = v;
+    if (qh) qh[i] = __float2bfloat16_rn(v);
+  }
+}
+
+template <typename T>
+__global__ void reconstruct_kernel(const T* __restrict__ x, int ld, int d, int64_t i0, int64_t n,
+                                   float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = n * (int64_t)d;
+  for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / d;
+    int c = (int)(i - r * d);
+    out[i] = (float)x[(i0 + r) * (int64_t)ld + c];
+  }
+}
+
+// ---- exact exhaustive scan ----------------------------------------------------------------------
+// Each warp owns a private top-k list (replace-min) per selected query; a global per-query key
+// threshold (tau_g, atomicMax) lets every warp skip rows that already lost somewhere else.
+constexpr int kExactF = 8;  // queries scored per corpus pass
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uint64_t t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void warp_list_insert(volatile uint64_t* list, int k, int& cnt, uint64_t& minkey,
+                                                 uint64_t key, int lane) {
+  if (cnt < k) {
+    if (lane == 0) list[cnt] = key;
+    cnt++;
+  } else {
+    for (int i = lane; i < k; i += 32)
+      if (list[i] == minkey) list[i] = key;
+  }
+  __syncwarp();
+  if (cnt == k) {
+    uint64_t m = ~0ull;
+    for (int i = lane; i < k; i += 32) {
+      uint64_t v = list[i];
+      m = v < m ? v : m;
+    }
+    minkey = warp_min_u64(m);
+  }
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256)
+exact_scan_kernel(const T* __restrict__ x, int64_t N, int ld, const float* __restrict__ qpad,
+                  const int* __restrict__ qsel, int nsel, int k, uint64_t* __restrict__ lists,
+                  int* __restrict__ cnts, unsigned long long* __restrict__ tau_g) {
+  extern __shared__ __align__(16) float qs[];  // [kExactF][ld]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int64_t W = (int64_t)gridDim.x * wpb;
+  const int64_t gw = (int64_t)blockIdx.x * wpb + wib;
+
+  for (int g0 = 0; g0 < nsel; g0 += kExactF) {
+    const int nf = min(kExactF, nsel - g0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kExactF * ld; i += blockDim.x) {
+      int f = i / ld, c = i - f * ld;
+      qs[i] = (f < nf) ? qpad[(int64_t)qsel[g0 + f] * ld + c] : 0.f;
+    }
+    __syncthreads();
+
+    int cnt[kExactF];
+    uint64_t minkey[kExactF], tg[kExactF];
+#pragma unroll
+    for (int f = 0; f < kExactF; ++f) {
+      cnt[f] = 0;
+      minkey[f] = 0;
+      tg[f] = 0;
+    }
+    int it = 0;
+    for (int64_t r = gw; r < N; r += W, ++it) {
+      if ((it & 15) == 0) {
+#pragma unroll
+        for (int f = 0; f < kExactF; ++f)
+          if (f < nf) tg[f] = *((volatile unsigned long long*)&tau_g[g0 + f]);
+      }
+      float sc[kExactF];
+      warp_exact_scores<T, METRIC, kExactF>(x + r * (int64_t)ld, qs, ld, ld, lane, sc);
+#pragma unroll
+      for (int f = 0; f < kExactF; ++f) {
+        if (f < nf) {
+          float s = (METRIC == kMetricIP) ? sc[f] : -sc[f];
+          uint64_t key = make_key(s, (uint32_t)r);
+          uint64_t thr = (cnt[f] == k) ? (minkey[f] > tg[f] ? minkey[f] : tg[f]) : tg[f];
+          if (key > thr) {
+            volatile uint64_t* lst = lists + ((int64_t)(g0 + f) * W + gw) * k;
+            warp_list_insert(lst, k, cnt[f], minkey[f], key, lane);
+            if (cnt[f] == k && minkey[f] > tg[f]) {
+              if (lane == 0) atomicMax(&tau_g[g0 + f], (unsigned long long)minkey[f]);
+              tg[f] = minkey[f];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < kExactF; ++f)
+      if (f < nf && lane == 0) cnts[(int64_t)(g0 + f) * W + gw] = cnt[f];
+  }
+}
+
+// One block per selected query: gather the warps' lists, keep keys >= tau_g, sort, write top-k.
+constexpr int kMergeCap = 4096;
+
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+exact_merge_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ cnts,
+                   const unsigned long long* __restrict__ tau_g, const int* __restrict__ qsel, int64_t W, int k,
+                   int64_t id_base, float* __restrict__ D, int64_t* __restrict__ I) {
+  __shared__ uint64_t buf[kMergeCap];
+  __shared__ int s_n;
+  __shared__ unsigned long long s_best;
+  const int f = blockIdx.x;
+  const int q = qsel[f];
+  const uint64_t thr = tau_g[f];
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const int64_t total = W * k;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    int64_t w = i / k;
+    int j = (int)(i - w * k);
+    if (j < cnts[(int64_t)f * W + w]) {
+      uint64_t key = lists[((int64_t)f * W + w) * k + j];
+      if (key >= thr) {
+        int slot = atomicAdd(&s_n, 1);
+        if (slot < kMergeCap) buf[slot] = key;
+      }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  float* Dq = D + (int64_t)q * k;
+  int64_t* Iq = I + (int64_t)q * k;
+  const float pad = (METRIC == kMetricIP) ? HR_NEG_INF : -HR_NEG_INF;
+  if (n <= kMergeCap) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    for (int i = n + threadIdx.x; i < p; i += blockDim.x) buf[i] = 0;
+    block_bitonic_desc(buf, p);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      if (j < n) {
+        float s = key_score(buf[j]);
+        Dq[j] = (METRIC == kMetricIP) ? s : -s;
+        Iq[j] = (int64_t)key_row(buf[j]) + id_base;
+      } else {
+        Dq[j] = pad;
+        Iq[j] = -1;
+      }
+    }
+  } else {
+    // rare: more surviving keys than the sort buffer holds -> k rounds of "largest key below the last"
+    unsigned long long last = ~0ull;
+    for (int j = 0; j < k; ++j) {
+      if (threadIdx.x == 0) s_best = 0;
+      __syncthreads();
+      unsigned long long best = 0;
+      for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+        int64_t w = i / k;
+        int jj = (int)(i - w * k);
+        if (jj < cnts[(int64_t)f * W + w]) {
+          unsigned long long key = lists[((int64_t)f * W + w) * k + jj];
+          if (key < last && key > best) best = key;
+        }
+      }
+      atomicMax(&s_best, best);
+      __syncthreads();
+      unsigned long long b = s_best;
+      if (threadIdx.x == 0) {
+        if (b != 0) {
+          float s = key_score(b);
+          Dq[j] = (METRIC == kMetricIP) ? s : -s;
+          Iq[j] = (int64_t)key_row(b) + id_base;
+        } else {
+          Dq[j] = pad;
+          Iq[j] = -1;
+        }
+      }
+      last = b ? b : 0;
+      __syncthreads();
+    }
+  }
+}
+
+// ---- exact re-score of the filter shortlist + final top-k + certificate ---------------------------
+// One block (256 threads) per query.  short_rows [nq][KL] (0xFFFFFFFF = empty), short_n [nq],
+// tprime [nq] = upper bound on the APPROXIMATE score of every row that is not in the shortlist
+// (HR_NEG_INF when nothing was dropped).  A query is certified when its exact k-th best, mapped to
+// the filter's score domain, beats tprime by more than the filter's worst-case error eps.
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256)
+rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict__ qpad,
+                        const uint32_t* __restrict__ short_rows, const int* __restrict__ short_n,
+                        const float* __restrict__ tprime, int KL, int k, float c_rel,
+                        const unsigned int* __restrict__ max_norm2_ord, int64_t id_base, float* __restrict__ D,
+                        int64_t* __restrict__ I, int* __restrict__ flagged, int* __restrict__ nflag) {
+  extern __shared__ uint64_t skeys[];  // [KL]
+  __shared__ float s_qn2;
+  __shared__ float s_ek;
+  __shared__ int s_have_k;
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarp = blockDim.x >> 5;
+  const int n = min(short_n[q], KL);
+  const float* qv = qpad + (int64_t)q * ld;
+  if (threadIdx.x == 0) s_have_k = 0;
+  if (warp == 0) {
+    float a = 0.f;
+    for (int c = lane; c < ld; c += 32) a = fmaf(qv[c], qv[c], a);
+    a = warp_sum_xor(a);
+    if (lane == 0) s_qn2 = a;
+  }
+  for (int i = warp; i < n; i += nwarp) {
+    uint32_t row = short_rows[(int64_t)q * KL + i];
+    float sc[1];
+    warp_exact_scores<T, METRIC, 1>(x + (int64_t)row * ld, qv, ld, ld, lane, sc);
+    if (lane == 0) skeys[i] = make_key(METRIC == kMetricIP ? sc[0] : -sc[0], row);
+  }
+  __syncthreads();
+  float* Dq = D + (int64_t)q * k;
+  int64_t* Iq = I + (int64_t)q * k;
+  const float pad = (METRIC == kMetricIP) ? HR_NEG_INF : -HR_NEG_INF;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    uint64_t me = skeys[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (skeys[j] > me);
+    if (rank < k) {
+      float s = key_score(me);
+      Dq[rank] = (METRIC == kMetricIP) ? s : -s;
+      Iq[rank] = (int64_t)key_row(me) + id_base;
+      if (rank == k - 1) {
+        s_ek = s;
+        s_have_k = 1;
+      }
+    }
+  }
+  for (int j = n + threadIdx.x; j < k; j += blockDim.x) {
+    Dq[j] = pad;
+    Iq[j] = -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float tp = tprime[q];
+    bool ok;
+    if (tp <= HR_NEG_INF) {
+      ok = true;  // nothing was ever dropped: the shortlist is the whole index
+    } else if (!s_have_k) {
+      ok = false;  // rows were dropped but fewer than k survived: cannot certify
+    } else {
+      const float xn = sqrtf(ord2f(*max_norm2_ord));
+      const float qn = sqrtf(s_qn2);
+      float eps = c_rel * qn * xn + 1e-6f * (s_qn2 + xn * xn) + 1e-30f;
+      // map the exact k-th best into the filter's score domain
+      float shat = (METRIC == kMetricIP) ? s_ek : 0.5f * (s_qn2 + s_ek);  // s_ek = -dist for L2
+      ok = shat > tp + eps;
+    }
+    if (!ok) {
+      int slot = atomicAdd(nflag, 1);
+      flagged[slot] = q;
+    }
+  }
+}
+
+}  // namespace hr

@@ -1,0 +1,336 @@
+// dense_scan_tc.cuh — the dense filter scan: query x corpus inner products on the 5th-gen tensor
+// cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA, with the per-query top-KL
+// selection fused into the epilogue so the score matrix never reaches HBM.
+//
+// Replaces the hot loop of faiss::IndexFlat::search called at
+// /root/reference/rag/storage/faiss_index.py:83 (N*d FMAs + N heap tests per query).
+//
+// GEMM shape:  D[128 queries, 256 corpus rows] = Q_tile[128, K] * X_tile[256, K]^T, both K-major.
+//   M (TMEM lanes)   = queries      -> one epilogue thread owns one query: thresholds in registers
+//   N (TMEM columns) = corpus rows  -> 2 accumulator stages x 256 columns = all 512 TMEM columns
+//   K                = d, streamed in 128-byte blocks (32 tf32 / 64 bf16 elements), 4-stage ring
+// Persistent CTAs (one per SM): CTA b owns corpus tiles b, b+G, ... and, for each, loops over the
+// query tiles, so a corpus tile is fetched from HBM once and re-read from L2 for nq > 128.
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue (warp w reads TMEM lanes 32*(w%4)..+31).
+//
+// Epilogue selection: thread (query) keeps a private candidate list of KL (score,row) entries in
+// global memory (L2 resident) with replace-min insertion, a local threshold tau_l (its KL-th best)
+// and a cross-CTA threshold tau_g[q] (atomicMax of every CTA's tau_l).  A score is inserted only if
+// it beats max(tau_l, tau_g); the common case is one FMNMX per score and one compare per 32.
+// Invariant used by the certificate (dense_exact.cuh): every row that is NOT in some list at the
+// end has approximate score <= final tau_g[q].
+#pragma once
+#include "common.cuh"
+
+namespace hr {
+
+constexpr int kScanBM = 128;
+constexpr int kScanBN = 256;
+constexpr int kScanStages = 4;
+constexpr int kScanABytes = kScanBM * 128;
+constexpr int kScanBBytes = kScanBN * 128;
+constexpr int kScanStageBytes = kScanABytes + kScanBBytes;
+constexpr int kScanNqMax = 2048;  // queries per launch (per-query state lives in shared memory)
+constexpr int kScanThreads = 256;
+
+struct ScanSmemTail {
+  uint64_t full_bar[kScanStages];
+  uint64_t empty_bar[kScanStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_ptr;
+  uint32_t pad_[3];
+  float half_norms[2][kScanBN];
+  float tau_l[kScanNqMax];
+  uint16_t cnt[kScanNqMax];
+  uint16_t minpos[kScanNqMax];
+};
+constexpr int kScanSmemBytes = kScanStages * kScanStageBytes + (int)sizeof(ScanSmemTail) + 1024;
+
+struct ScanParams {
+  int64_t N;        // corpus rows
+  int nq;           // queries in this launch (<= kScanNqMax)
+  int kblocks;      // 128-byte K blocks per row (ld * elem_size / 128)
+  int KL;           // candidate list length
+  int num_ctiles;   // ceil(N / 256)
+  int num_qtiles;   // ceil(nq / 128)
+  const float* norms;  // |x|^2 per row (L2 only)
+  Cand* lists;         // [gridDim.x][nq][KL]
+  int* cnts;           // [gridDim.x][nq]
+  unsigned int* tau_g; // [nq] ordered-uint threshold, 0 = unset
+};
+
+__device__ __noinline__ void cand_insert(Cand* list, int KL, float v, uint32_t row, float& tau_l, uint32_t& cnt,
+                                         uint32_t& minpos, float& thr, float tg, unsigned int* tau_g_slot) {
+  Cand c;
+  c.s = v;
+  c.row = row;
+  if (cnt < (uint32_t)KL) {
+    list[cnt] = c;
+    cnt++;
+    if (cnt < (uint32_t)KL) return;
+  } else {
+    list[minpos] = c;
+  }
+  float m = list[0].s;
+  uint32_t mp = 0;
+  for (int i = 1; i < KL; ++i) {
+    float s = list[i].s;
+    if (s < m) {
+      m = s;
+      mp = i;
+    }
+  }
+  tau_l = m;
+  minpos = mp;
+  if (m > tg) atomicMax(tau_g_slot, f2ord(m));
+  thr = fmaxf(m, tg);
+}
+
+// KIND 0: fp32 storage, kind::tf32 (32 elements per K block).  KIND 1: bf16 storage, kind::f16.
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+               const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  ScanSmemTail* st = (ScanSmemTail*)(smem + kScanStages * kScanStageBytes);
+  constexpr int kKElems = (KIND == 0) ? 32 : 64;
+  constexpr uint32_t kIdesc = umma_idesc(KIND == 0 ? 2u : 1u, kScanBM, kScanBN);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kScanStages; ++s) {
+      mbar_init(&st->full_bar[s], 1);
+      mbar_init(&st->empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&st->tmem_full[a], 1);
+      mbar_init(&st->tmem_empty[a], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&st->tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kScanNqMax; i += blockDim.x) {
+    st->tau_l[i] = HR_NEG_INF;
+    st->cnt[i] = 0;
+    st->minpos[i] = 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = st->tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = blockIdx.x; c < p.num_ctiles; c += gridDim.x) {
+        for (int m = 0; m < p.num_qtiles; ++m) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&st->empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&st->full_bar[stage], kScanStageBytes);
+            uint8_t* sa = smem + stage * kScanStageBytes;
+            tma_load_2d(sa, &tmap_q, &st->full_bar[stage], kb * kKElems, m * kScanBM);
+            tma_load_2d(sa + kScanABytes, &tmap_x, &st->full_bar[stage], kb * kKElems, c * kScanBN);
+            if (++stage == kScanStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int c = blockIdx.x; c < p.num_ctiles; c += gridDim.x) {
+        for (int m = 0; m < p.num_qtiles; ++m, ++it) {
+          const uint32_t as = it & 1u;
+          const uint32_t aphase = (it >> 1) & 1u;
+          mbar_wait(&st->tmem_empty[as], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * kScanBN;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&st->full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kScanStageBytes);
+            const uint64_t adesc = umma_desc_sw128(sa);
+            const uint64_t bdesc = umma_desc_sw128(sa + kScanABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // advance 32 bytes of K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+              if (KIND == 0)
+                tc_mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (uint32_t)((kb | k) != 0));
+              else
+                tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (uint32_t)((kb | k) != 0));
+            }
+            tc_commit(&st->empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (++stage == kScanStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit(&st->tmem_full[as]);  // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: fused per-query top-KL =====================
+    const int ew = warp & 3;
+    const int et = threadIdx.x - 128;
+    uint32_t it = 0;
+    uint32_t cit = 0;
+    for (int c = blockIdx.x; c < p.num_ctiles; c += gridDim.x, ++cit) {
+      const int nb = cit & 1;
+      if (METRIC == 1) {
+        for (int j = et; j < kScanBN; j += 128) {
+          int64_t row = (int64_t)c * kScanBN + j;
+          st->half_norms[nb][j] = row < p.N ? 0.5f * p.norms[row] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const int64_t rem = p.N - (int64_t)c * kScanBN;
+      const int col_limit = rem < kScanBN ? (int)rem : kScanBN;
+      const uint32_t row0 = (uint32_t)c * kScanBN;
+      for (int m = 0; m < p.num_qtiles; ++m, ++it) {
+        const uint32_t as = it & 1u;
+        const uint32_t aphase = (it >> 1) & 1u;
+        const int q = m * kScanBM + ew * 32 + lane;
+        const bool active = q < p.nq;
+        float tau_l = HR_NEG_INF, tg = HR_NEG_INF, thr = HR_NEG_INF;
+        uint32_t cnt = 0, minpos = 0;
+        Cand* list = nullptr;
+        if (active) {
+          tau_l = st->tau_l[q];
+          cnt = st->cnt[q];
+          minpos = st->minpos[q];
+          unsigned int o = *((volatile unsigned int*)&p.tau_g[q]);
+          tg = o ? ord2f(o) : HR_NEG_INF;
+          thr = (cnt == (uint32_t)p.KL) ? fmaxf(tau_l, tg) : tg;
+          list = p.lists + ((size_t)blockIdx.x * p.nq + q) * p.KL;
+        }
+        mbar_wait(&st->tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+        for (int ch = 0; ch < kScanBN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          if (active) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __uint_as_float(r[j]);
+              if (METRIC == 1) v[j] -= st->half_norms[nb][ch * 32 + j];
+            }
+            const int cbase = ch * 32;
+            if (cbase + 32 <= col_limit) {
+              float mx = v[0];
+#pragma unroll
+              for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+              if (mx > thr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (v[j] > thr)
+                    cand_insert(list, p.KL, v[j], row0 + cbase + j, tau_l, cnt, minpos, thr, tg, &p.tau_g[q]);
+              }
+            } else if (cbase < col_limit) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < col_limit && v[j] > thr)
+                  cand_insert(list, p.KL, v[j], row0 + cbase + j, tau_l, cnt, minpos, thr, tg, &p.tau_g[q]);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&st->tmem_empty[as]);
+        if (active) {
+          st->tau_l[q] = tau_l;
+          st->cnt[q] = (uint16_t)cnt;
+          st->minpos[q] = (uint16_t)minpos;
+        }
+      }
+    }
+    for (int q = et; q < p.nq; q += 128) p.cnts[(size_t)blockIdx.x * p.nq + q] = st->cnt[q];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- merge of the per-CTA candidate lists -> shortlist for the exact re-score -------------------
+// One block per query.  Keeps entries with score >= T* (= final tau_g), sorts them by key, emits
+// the best KL rows and tprime = upper bound on the approximate score of everything left out.
+constexpr int kShortCap = 2048;
+
+__global__ void __launch_bounds__(256)
+scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
+                  const unsigned int* __restrict__ tau_g, int G, int nq, int KL,
+                  uint32_t* __restrict__ short_rows, int* __restrict__ short_n, float* __restrict__ tprime,
+                  int* __restrict__ overflow_count) {
+  __shared__ uint64_t buf[kShortCap];
+  __shared__ int s_n;
+  const int q = blockIdx.x;
+  const unsigned int o = tau_g[q];
+  const float tstar = o ? ord2f(o) : HR_NEG_INF;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const int total = G * KL;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int g = i / KL, j = i - g * KL;
+    if (j < cnts[(size_t)g * nq + q]) {
+      Cand c = lists[((size_t)g * nq + q) * KL + j];
+      if (c.s >= tstar) {
+        int slot = atomicAdd(&s_n, 1);
+        if (slot < kShortCap) buf[slot] = make_key(c.s, c.row);
+      }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  uint32_t* out = short_rows + (size_t)q * KL;
+  if (n > kShortCap) {  // cannot rank: send the query to the exact fallback
+    if (threadIdx.x == 0) {
+      short_n[q] = 0;
+      tprime[q] = -HR_NEG_INF;
+      atomicAdd(overflow_count, 1);
+    }
+    for (int j = threadIdx.x; j < KL; j += blockDim.x) out[j] = 0xFFFFFFFFu;
+    return;
+  }
+  int pw = 1;
+  while (pw < n) pw <<= 1;
+  for (int i = n + threadIdx.x; i < pw; i += blockDim.x) buf[i] = 0;
+  block_bitonic_desc(buf, pw);
+  for (int j = threadIdx.x; j < KL; j += blockDim.x) out[j] = (j < n) ? key_row(buf[j]) : 0xFFFFFFFFu;
+  if (threadIdx.x == 0) {
+    short_n[q] = n < KL ? n : KL;
+    float tp = HR_NEG_INF;
+    if (o) tp = tstar;                                  // rows dropped by a threshold are <= T*
+    if (n > KL) tp = fmaxf(tp, key_score(buf[KL]));     // best list entry that was left out
+    tprime[q] = tp;
+  }
+}
+
+}  // namespace hr

@@ -1,0 +1,135 @@
+// fuse.cuh — hybrid fusion (weighted-score / RRF), final top-k, and the cross-shard k-way merge.
+// Latency-bound warp/block-primitive kernels on (nq x a few hundred) candidates.
+//
+// Definitions: oracle/fusion.py.  Only reference-side pins: the weights
+// 0.7 / 0.3 (rag/config.py:44-45) and the dense transform clamp(1 - d/2, 0, 1)
+// (rag/storage/faiss_index.py:86-88).  Order everywhere: (score desc, id asc).
+#pragma once
+#include "common.cuh"
+
+namespace hr {
+
+constexpr int kFuseMaxKc = 256;
+
+// better(a,b): a ranks strictly before b
+__device__ __forceinline__ bool ranks_before(float sa, int64_t ia, float sb, int64_t ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+// One block per query.  Entries [0,kc) = dense list, [kc,2kc) = sparse list (only sparse-only docs valid).
+__global__ void __launch_bounds__(256)
+fuse_kernel(const float* __restrict__ dD, const int64_t* __restrict__ dI, const float* __restrict__ bS,
+            const int64_t* __restrict__ bI, const float* __restrict__ bmax, int kc, int top_k, int metric,
+            int mode, float w_vec, float w_bm25, float* __restrict__ oS, int64_t* __restrict__ oI) {
+  __shared__ float fs[2 * kFuseMaxKc];
+  __shared__ int64_t fid[2 * kFuseMaxKc];
+  __shared__ int s_valid;
+  const int q = blockIdx.x;
+  const float* dDq = dD + (size_t)q * kc;
+  const int64_t* dIq = dI + (size_t)q * kc;
+  const float* bSq = bS + (size_t)q * kc;
+  const int64_t* bIq = bI + (size_t)q * kc;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  float mx = 0.f;
+  if (bmax) mx = bmax[q];
+  else if (bIq[0] >= 0) mx = bSq[0];  // lists are best-first
+  const int n2 = 2 * kc;
+  for (int e = threadIdx.x; e < n2; e += blockDim.x) {
+    float f = 0.f;
+    int64_t id = -1;
+    if (e < kc) {
+      id = dIq[e];
+      if (id >= 0) {
+        int sp = -1;
+        for (int j = 0; j < kc; ++j)
+          if (bIq[j] == id) { sp = j; break; }
+        if (mode == 0) {
+          float sim = (metric == 1) ? (1.0f - dDq[e] * 0.5f) : dDq[e];
+          sim = fminf(1.0f, fmaxf(0.0f, sim));
+          f = w_vec * sim;
+          if (sp >= 0 && mx > 0.f) f = fmaf(w_bm25, bSq[sp] / mx, f);
+        } else {
+          f = 1.0f / (60.0f + (float)(e + 1));
+          if (sp >= 0) f += 1.0f / (60.0f + (float)(sp + 1));
+        }
+      }
+    } else {
+      const int j = e - kc;
+      id = bIq[j];
+      if (id >= 0) {
+        bool in_dense = false;
+        for (int i = 0; i < kc; ++i)
+          if (dIq[i] == id) { in_dense = true; break; }
+        if (in_dense) id = -1;
+        else if (mode == 0) f = (mx > 0.f) ? w_bm25 * (bSq[j] / mx) : 0.f;
+        else f = 1.0f / (60.0f + (float)(j + 1));
+      }
+    }
+    fs[e] = f;
+    fid[e] = id;
+    if (id >= 0) atomicAdd(&s_valid, 1);
+  }
+  __syncthreads();
+  const int nv = s_valid;
+  for (int e = threadIdx.x; e < n2; e += blockDim.x) {
+    const int64_t id = fid[e];
+    if (id < 0) continue;
+    const float f = fs[e];
+    int rank = 0;
+    for (int j = 0; j < n2; ++j) {
+      const int64_t oj = fid[j];
+      if (oj >= 0 && ranks_before(fs[j], oj, f, id)) rank++;
+    }
+    if (rank < top_k) {
+      oS[(size_t)q * top_k + rank] = f;
+      oI[(size_t)q * top_k + rank] = id;
+    }
+  }
+  for (int j = nv + threadIdx.x; j < top_k; j += blockDim.x) {
+    oS[(size_t)q * top_k + j] = 0.f;
+    oI[(size_t)q * top_k + j] = -1;
+  }
+}
+
+// k-way merge of candidate lists: S,I [nq][n_cand] -> best k (largest or smallest first), id asc ties.
+constexpr int kMergeTopkCap = 2048;
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, int n_cand, int k, int largest,
+                  float pad_score, float* __restrict__ oS, int64_t* __restrict__ oI) {
+  __shared__ float ss[kMergeTopkCap];
+  __shared__ int64_t si[kMergeTopkCap];
+  __shared__ int s_valid;
+  const int q = blockIdx.x;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_cand; e += blockDim.x) {
+    float s = S[(size_t)q * n_cand + e];
+    int64_t id = I[(size_t)q * n_cand + e];
+    ss[e] = largest ? s : -s;
+    si[e] = id;
+    if (id >= 0) atomicAdd(&s_valid, 1);
+  }
+  __syncthreads();
+  const int nv = s_valid;
+  for (int e = threadIdx.x; e < n_cand; e += blockDim.x) {
+    const int64_t id = si[e];
+    if (id < 0) continue;
+    const float f = ss[e];
+    int rank = 0;
+    for (int j = 0; j < n_cand; ++j) {
+      const int64_t oj = si[j];
+      if (oj >= 0 && ranks_before(ss[j], oj, f, id)) rank++;
+    }
+    if (rank < k) {
+      oS[(size_t)q * k + rank] = largest ? f : -f;
+      oI[(size_t)q * k + rank] = id;
+    }
+  }
+  for (int j = nv + threadIdx.x; j < k; j += blockDim.x) {
+    oS[(size_t)q * k + j] = pad_score;
+    oI[(size_t)q * k + j] = -1;
+  }
+}
+
+}  // namespace hr

@@ -1,0 +1,987 @@
+// hr_api.cu — C ABI of libhr_b200.so (declared in include/hr_b200.h).
+// Host-side orchestration only: device memory, tensor maps, launches, error codes.
+// There is NO CPU compute path in this file: without a CUDA device every entry point fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hr_b200.h"
+#include "common.cuh"
+#include "dense_exact.cuh"
+#include "dense_scan_tc.cuh"
+#include "bm25.cuh"
+#include "fuse.cuh"
+
+using namespace hr;
+
+// -------------------------------------------------------------------------------------------------
+// errors, launch accounting
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int set_err(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define HR_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _b[512];                                                                                \
+      snprintf(_b, sizeof _b, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,        \
+               __LINE__, cudaGetErrorString(_e));                                                  \
+      return set_err(_e == cudaErrorMemoryAllocation ? HR_ERR_NOMEM : HR_ERR_CUDA, _b);            \
+    }                                                                                              \
+  } while (0)
+#define HR_TRY(expr)             \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != HR_OK) return _r;  \
+  } while (0)
+#define HR_LAUNCHED()                 \
+  do {                                \
+    g_launches.fetch_add(1);          \
+    HR_CUDA(cudaGetLastError());      \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define HR_DEVICE(dev)                                                        \
+  DeviceGuard _guard(dev);                                                    \
+  if (!_guard.ok) return set_err(HR_ERR_CUDA, "no usable CUDA device (hr_b200 has no CPU fallback)")
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t n) {
+    if (n <= bytes) return HR_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return set_err(HR_ERR_NOMEM, "cudaMalloc of scratch failed");
+    }
+    bytes = want;
+    return HR_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return (T*)p; }
+};
+
+// -------------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched at run time: no link-time libcuda dependency)
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+// rows x (kblocks * 128 bytes) K-major matrix, box = {128 bytes, box_rows}, 128-byte swizzle
+static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int ld_elems, int elem_bytes, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return set_err(HR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)ld_elems, (cuuint64_t)(rows > 0 ? rows : 1)};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[128];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return set_err(HR_ERR_CUDA, b);
+  }
+  return HR_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// flat dense index
+// -------------------------------------------------------------------------------------------------
+struct RetrieveScratch {
+  DevBuf q, qi, qt, dD, dI, bS, bI, oS, oI;
+};
+
+struct hr_index {
+  RetrieveScratch rs;
+  int d = 0, ld = 0, metric = 0, storage = 0, device = 0, mode = HR_MODE_AUTO;
+  int elem = 4;
+  int num_sms = 148;
+  int64_t ntotal = 0, capacity = 0, id_base = 0;
+  void* x = nullptr;
+  float* norms = nullptr;
+  unsigned int* max_norm2 = nullptr;  // ordered-uint of max |x|^2
+  DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_n, tprime, flagged, counters;
+  DevBuf ex_lists, ex_cnts, ex_tau, ex_sel, io_q, io_D, io_I, stage;
+  int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  hr_scan_stats stats{};
+};
+
+static size_t row_bytes(const hr_index* h) { return (size_t)h->ld * h->elem; }
+
+extern "C" const char* hr_last_error(void) { return g_err.c_str(); }
+extern "C" int hr_version(void) { return 100; }
+extern "C" int64_t hr_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int hr_device_count(int* out) {
+  if (!out) return set_err(HR_ERR_INVALID, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    *out = 0;
+    return set_err(HR_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *out = n;
+  return HR_OK;
+}
+
+extern "C" int hr_index_create(int d, int metric, int storage_dtype, int device, hr_index** out) {
+  if (!out) return set_err(HR_ERR_INVALID, "null out");
+  *out = nullptr;
+  if (d <= 0 || d > 65536) return set_err(HR_ERR_INVALID, "d must be in [1, 65536]");
+  if (metric != HR_METRIC_INNER_PRODUCT && metric != HR_METRIC_L2)
+    return set_err(HR_ERR_INVALID, "metric must be METRIC_INNER_PRODUCT (0) or METRIC_L2 (1)");
+  if (storage_dtype != HR_STORAGE_F32 && storage_dtype != HR_STORAGE_BF16)
+    return set_err(HR_ERR_INVALID, "storage dtype must be HR_STORAGE_F32 or HR_STORAGE_BF16");
+  int ndev = 0;
+  HR_TRY(hr_device_count(&ndev));
+  if (ndev <= 0) return set_err(HR_ERR_CUDA, "no CUDA device (hr_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(HR_ERR_INVALID, "device ordinal out of range");
+  HR_DEVICE(device);
+  cudaDeviceProp prop;
+  HR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    char b[160];
+    snprintf(b, sizeof b, "device %d is sm_%d%d; libhr_b200 is built for sm_100a (B200) only", device, prop.major,
+             prop.minor);
+    return set_err(HR_ERR_CUDA, b);
+  }
+  hr_index* h = new hr_index();
+  h->d = d;
+  h->metric = metric;
+  h->storage = storage_dtype;
+  h->device = device;
+  h->elem = storage_dtype == HR_STORAGE_F32 ? 4 : 2;
+  const int kelems = 128 / h->elem;  // elements per 128-byte K block
+  h->ld = ((d + kelems - 1) / kelems) * kelems;
+  h->num_sms = prop.multiProcessorCount;
+  if (cudaMalloc((void**)&h->max_norm2, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(h->max_norm2, 0, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_counters, 4 * sizeof(int)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete h;
+    return set_err(HR_ERR_NOMEM, "allocation failed in hr_index_create");
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  *out = h;
+  return HR_OK;
+}
+
+extern "C" int hr_index_destroy(hr_index* h) {
+  if (!h) return HR_OK;
+  DeviceGuard g(h->device);
+  if (h->x) cudaFree(h->x);
+  if (h->norms) cudaFree(h->norms);
+  if (h->max_norm2) cudaFree(h->max_norm2);
+  if (h->h_counters) cudaFreeHost(h->h_counters);
+  DevBuf* bufs[] = {&h->qpad, &h->qh, &h->lists, &h->cnts, &h->tau_g, &h->short_rows, &h->short_n, &h->tprime,
+                    &h->flagged, &h->counters, &h->ex_lists, &h->ex_cnts, &h->ex_tau, &h->ex_sel, &h->io_q,
+                    &h->io_D, &h->io_I, &h->stage, &h->rs.q, &h->rs.qi, &h->rs.qt, &h->rs.dD, &h->rs.dI,
+                    &h->rs.bS, &h->rs.bI, &h->rs.oS, &h->rs.oI};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return HR_OK;
+}
+
+static int index_grow(hr_index* h, int64_t need, cudaStream_t st) {
+  if (need <= h->capacity) return HR_OK;
+  void* nx = nullptr;
+  float* nn = nullptr;
+  cudaError_t e = cudaMalloc(&nx, (size_t)need * row_bytes(h));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&nn, (size_t)need * sizeof(float));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (nx) cudaFree(nx);
+    return set_err(HR_ERR_NOMEM, "cudaMalloc failed while growing the index (corpus does not fit in HBM?)");
+  }
+  if (h->ntotal > 0) {
+    HR_CUDA(cudaMemcpyAsync(nx, h->x, (size_t)h->ntotal * row_bytes(h), cudaMemcpyDeviceToDevice, st));
+    HR_CUDA(cudaMemcpyAsync(nn, h->norms, (size_t)h->ntotal * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    HR_CUDA(cudaStreamSynchronize(st));
+  }
+  if (h->x) cudaFree(h->x);
+  if (h->norms) cudaFree(h->norms);
+  h->x = nx;
+  h->norms = nn;
+  h->capacity = need;
+  return HR_OK;
+}
+
+extern "C" int hr_index_reserve(hr_index* h, int64_t n_rows) {
+  if (!h) return set_err(HR_ERR_INVALID, "null index");
+  if (n_rows < 0 || n_rows >= (int64_t)0xFFFFFFF0ll) return set_err(HR_ERR_INVALID, "n_rows out of range");
+  HR_DEVICE(h->device);
+  return index_grow(h, n_rows, 0);
+}
+
+extern "C" int hr_index_add(hr_index* h, const float* x, int64_t n, int is_device, void* stream) {
+  if (!h) return set_err(HR_ERR_INVALID, "null index");
+  if (n < 0) return set_err(HR_ERR_INVALID, "n < 0");
+  if (n == 0) return HR_OK;
+  if (!x) return set_err(HR_ERR_INVALID, "null x");
+  if (h->ntotal + n >= (int64_t)0xFFFFFFF0ll) return set_err(HR_ERR_INVALID, "too many rows for one shard");
+  HR_DEVICE(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->ntotal + n > h->capacity) {
+    int64_t want = h->ntotal + n;
+    if (h->capacity > 0) want = std::max<int64_t>(want, h->capacity + h->capacity / 2);
+    HR_TRY(index_grow(h, want, st));
+  }
+  const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->d * 4));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+    const int64_t nr = std::min(chunk_rows, n - r0);
+    const float* src = x + r0 * (int64_t)h->d;
+    if (!is_device) {
+      HR_TRY(h->stage.ensure((size_t)nr * h->d * 4));
+      HR_CUDA(cudaMemcpyAsync(h->stage.p, src, (size_t)nr * h->d * 4, cudaMemcpyHostToDevice, st));
+      src = h->stage.as<float>();
+    }
+    const int64_t row0 = h->ntotal + r0;
+    const int blocks = (int)std::min<int64_t>((nr + 7) / 8, (int64_t)h->num_sms * 8);
+    if (h->storage == HR_STORAGE_F32)
+      convert_pad_norm_kernel<float><<<blocks, 256, 0, st>>>(src, nr, h->d, (float*)h->x + row0 * h->ld, h->ld,
+                                                            h->norms + row0, h->max_norm2);
+    else
+      convert_pad_norm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+          src, nr, h->d, (__nv_bfloat16*)h->x + row0 * h->ld, h->ld, h->norms + row0, h->max_norm2);
+    HR_LAUNCHED();
+    if (!is_device) HR_CUDA(cudaStreamSynchronize(st));  // staging buffer is reused
+  }
+  HR_CUDA(cudaStreamSynchronize(st));
+  h->ntotal += n;
+  return HR_OK;
+}
+
+extern "C" int hr_index_reset(hr_index* h) {
+  if (!h) return set_err(HR_ERR_INVALID, "null index");
+  HR_DEVICE(h->device);
+  h->ntotal = 0;
+  HR_CUDA(cudaMemset(h->max_norm2, 0, sizeof(unsigned int)));
+  return HR_OK;
+}
+extern "C" int64_t hr_index_ntotal(const hr_index* h) { return h ? h->ntotal : -1; }
+extern "C" int hr_index_d(const hr_index* h) { return h ? h->d : -1; }
+extern "C" int hr_index_metric(const hr_index* h) { return h ? h->metric : -1; }
+extern "C" int hr_index_storage(const hr_index* h) { return h ? h->storage : -1; }
+extern "C" int hr_index_set_id_base(hr_index* h, int64_t id_base) {
+  if (!h) return set_err(HR_ERR_INVALID, "null index");
+  h->id_base = id_base;
+  return HR_OK;
+}
+extern "C" int hr_index_set_mode(hr_index* h, int mode) {
+  if (!h) return set_err(HR_ERR_INVALID, "null index");
+  if (mode != HR_MODE_AUTO && mode != HR_MODE_EXACT_SIMT) return set_err(HR_ERR_INVALID, "unknown mode");
+  h->mode = mode;
+  return HR_OK;
+}
+extern "C" int hr_index_last_stats(const hr_index* h, hr_scan_stats* out) {
+  if (!h || !out) return set_err(HR_ERR_INVALID, "null argument");
+  *out = h->stats;
+  return HR_OK;
+}
+
+extern "C" int hr_index_debug_dump(hr_index* h, int64_t nq, void* lists, int32_t* cnts, uint32_t* tau,
+                                   uint32_t* short_rows, float* tprime) {
+  if (!h) return set_err(HR_ERR_INVALID, "null index");
+  HR_DEVICE(h->device);
+  const int64_t G = h->stats.grid, KL = h->stats.list_len;
+  if (h->stats.mode_used != HR_MODE_AUTO || G <= 0 || nq <= 0 || nq > kScanNqMax)
+    return set_err(HR_ERR_INVALID, "debug_dump: last search did not run the filter scan");
+  HR_CUDA(cudaDeviceSynchronize());
+  if (lists) HR_CUDA(cudaMemcpy(lists, h->lists.p, (size_t)G * nq * KL * sizeof(Cand), cudaMemcpyDeviceToHost));
+  if (cnts) HR_CUDA(cudaMemcpy(cnts, h->cnts.p, (size_t)G * nq * 4, cudaMemcpyDeviceToHost));
+  if (tau) HR_CUDA(cudaMemcpy(tau, h->tau_g.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+  if (short_rows) HR_CUDA(cudaMemcpy(short_rows, h->short_rows.p, (size_t)nq * KL * 4, cudaMemcpyDeviceToHost));
+  if (tprime) HR_CUDA(cudaMemcpy(tprime, h->tprime.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+  return HR_OK;
+}
+
+extern "C" int hr_index_reconstruct(hr_index* h, int64_t i0, int64_t n, float* out_host) {
+  if (!h || !out_host) return set_err(HR_ERR_INVALID, "null argument");
+  if (i0 < 0 || n < 0 || i0 + n > h->ntotal) return set_err(HR_ERR_INVALID, "reconstruct: row range out of bounds");
+  if (n == 0) return HR_OK;
+  HR_DEVICE(h->device);
+  const int64_t chunk = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->d * 4));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t nr = std::min(chunk, n - r0);
+    HR_TRY(h->stage.ensure((size_t)nr * h->d * 4));
+    const int blocks = (int)std::min<int64_t>((nr * h->d + 255) / 256, 4096);
+    if (h->storage == HR_STORAGE_F32)
+      reconstruct_kernel<float><<<blocks, 256>>>((const float*)h->x, h->ld, h->d, i0 + r0, nr, h->stage.as<float>());
+    else
+      reconstruct_kernel<__nv_bfloat16><<<blocks, 256>>>((const __nv_bfloat16*)h->x, h->ld, h->d, i0 + r0, nr,
+                                                         h->stage.as<float>());
+    HR_LAUNCHED();
+    HR_CUDA(cudaMemcpy(out_host + r0 * (int64_t)h->d, h->stage.p, (size_t)nr * h->d * 4, cudaMemcpyDeviceToHost));
+  }
+  return HR_OK;
+}
+
+// ---- search -------------------------------------------------------------------------------------
+__global__ void fill_pad_kernel(float* D, int64_t* I, int64_t n, float pad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    D[i] = pad;
+    I[i] = -1;
+  }
+}
+__global__ void iota_kernel(int* a, int n, int base) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = base + i;
+}
+
+static int list_len_for_k(int k) {
+  if (k <= 16) return 32;
+  if (k <= 32) return 64;
+  if (k <= 64) return 128;
+  return 256;
+}
+
+template <typename T>
+static int launch_exact(hr_index* h, const int* qsel_dev, int nsel, int k, float* D, int64_t* I, cudaStream_t st) {
+  // exhaustive exact scan of the queries listed in qsel_dev (device), results written to D/I rows qsel[i]
+  const int grid = h->num_sms;
+  const int64_t W = (int64_t)grid * 8;
+  int fsel = std::max(kExactF, std::min(64, (64 * 128 / std::max(k, 1)) / kExactF * kExactF));
+  HR_TRY(h->ex_lists.ensure((size_t)fsel * W * k * 8));
+  HR_TRY(h->ex_cnts.ensure((size_t)fsel * W * 4));
+  HR_TRY(h->ex_tau.ensure((size_t)fsel * 8));
+  const size_t smem = (size_t)kExactF * h->ld * 4;
+  if (smem > 200 * 1024) return set_err(HR_ERR_INVALID, "d too large for the exact scan kernel");
+  for (int g0 = 0; g0 < nsel; g0 += fsel) {
+    const int ns = std::min(fsel, nsel - g0);
+    HR_CUDA(cudaMemsetAsync(h->ex_tau.p, 0, (size_t)ns * 8, st));
+    if (h->metric == HR_METRIC_INNER_PRODUCT) {
+      HR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<T, kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+      exact_scan_kernel<T, kMetricIP><<<grid, 256, smem, st>>>(
+          (const T*)h->x, h->ntotal, h->ld, h->qpad.as<float>(), qsel_dev + g0, ns, k, h->ex_lists.as<uint64_t>(),
+          h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>());
+      HR_LAUNCHED();
+      exact_merge_kernel<kMetricIP><<<ns, 256, 0, st>>>(h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(),
+                                                        h->ex_tau.as<unsigned long long>(), qsel_dev + g0, W, k,
+                                                        h->id_base, D, I);
+      HR_LAUNCHED();
+    } else {
+      HR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<T, kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+      exact_scan_kernel<T, kMetricL2><<<grid, 256, smem, st>>>(
+          (const T*)h->x, h->ntotal, h->ld, h->qpad.as<float>(), qsel_dev + g0, ns, k, h->ex_lists.as<uint64_t>(),
+          h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>());
+      HR_LAUNCHED();
+      exact_merge_kernel<kMetricL2><<<ns, 256, 0, st>>>(h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(),
+                                                        h->ex_tau.as<unsigned long long>(), qsel_dev + g0, W, k,
+                                                        h->id_base, D, I);
+      HR_LAUNCHED();
+    }
+  }
+  return HR_OK;
+}
+
+template <int KIND, int METRIC>
+static int launch_scan(hr_index* h, const CUtensorMap& tq, const CUtensorMap& tx, const ScanParams& p, int grid,
+                       cudaStream_t st) {
+  HR_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KIND, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kScanSmemBytes));
+  scan_tc_kernel<KIND, METRIC><<<grid, kScanThreads, kScanSmemBytes, st>>>(tq, tx, p);
+  HR_LAUNCHED();
+  return HR_OK;
+}
+
+template <typename T>
+static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_rel, float* D, int64_t* I, cudaStream_t st) {
+  const size_t smem = (size_t)KL * 8;
+  if (h->metric == HR_METRIC_INNER_PRODUCT)
+    rescore_finalize_kernel<T, kMetricIP><<<nb, 256, smem, st>>>(
+        (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
+        h->tprime.as<float>(), KL, k, c_rel, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(),
+        h->counters.as<int>());
+  else
+    rescore_finalize_kernel<T, kMetricL2><<<nb, 256, smem, st>>>(
+        (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
+        h->tprime.as<float>(), KL, k, c_rel, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(),
+        h->counters.as<int>());
+  HR_LAUNCHED();
+  return HR_OK;
+}
+
+// q_dev: fp32 [nq, d] on device; D_dev/I_dev: [nq, k] on device.  Synchronises `st` before returning.
+static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                            cudaStream_t st) {
+  const long long launches0 = g_launches.load();
+  h->stats = hr_scan_stats{};
+  const float pad = h->metric == HR_METRIC_INNER_PRODUCT ? HR_NEG_INF : -HR_NEG_INF;
+  if (nq == 0) return HR_OK;
+  cudaEventRecord(h->ev[0], st);
+  if (h->ntotal == 0) {
+    fill_pad_kernel<<<(int)std::min<int64_t>((nq * k + 255) / 256, 1024), 256, 0, st>>>(D_dev, I_dev, nq * k, pad);
+    HR_LAUNCHED();
+    HR_CUDA(cudaStreamSynchronize(st));
+    h->stats.launches = g_launches.load() - launches0;
+    return HR_OK;
+  }
+  const bool use_tc = (h->mode == HR_MODE_AUTO) && k <= 128;
+  const int KL = list_len_for_k(k);
+  const int num_ctiles = (int)((h->ntotal + kScanBN - 1) / kScanBN);
+  const int grid = std::min(num_ctiles, h->num_sms);
+  h->stats.mode_used = use_tc ? HR_MODE_AUTO : HR_MODE_EXACT_SIMT;
+  h->stats.list_len = use_tc ? KL : k;
+  h->stats.grid = use_tc ? grid : h->num_sms;
+  float scan_ms_total = 0.f;
+
+  for (int64_t q0 = 0; q0 < nq; q0 += kScanNqMax) {
+    const int nb = (int)std::min<int64_t>(kScanNqMax, nq - q0);
+    float* Db = D_dev + q0 * k;
+    int64_t* Ib = I_dev + q0 * k;
+    HR_TRY(h->qpad.ensure((size_t)nb * h->ld * 4));
+    if (h->storage == HR_STORAGE_BF16) HR_TRY(h->qh.ensure((size_t)nb * h->ld * 2));
+    {
+      const int64_t tot = (int64_t)nb * h->ld;
+      pad_queries_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 2048), 256, 0, st>>>(
+          q_dev + q0 * h->d, nb, h->d, h->ld, h->qpad.as<float>(),
+          h->storage == HR_STORAGE_BF16 ? h->qh.as<__nv_bfloat16>() : nullptr);
+      HR_LAUNCHED();
+    }
+    HR_TRY(h->ex_sel.ensure((size_t)nb * 4));
+    if (!use_tc) {
+      iota_kernel<<<(nb + 255) / 256, 256, 0, st>>>(h->ex_sel.as<int>(), nb, 0);
+      HR_LAUNCHED();
+      if (h->storage == HR_STORAGE_F32) HR_TRY(launch_exact<float>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st));
+      else HR_TRY(launch_exact<__nv_bfloat16>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st));
+      continue;
+    }
+    // ---- tensor-core filter scan ----
+    HR_TRY(h->lists.ensure((size_t)grid * nb * KL * sizeof(Cand)));
+    HR_TRY(h->cnts.ensure((size_t)grid * nb * 4));
+    HR_TRY(h->tau_g.ensure((size_t)nb * 4));
+    HR_TRY(h->short_rows.ensure((size_t)nb * KL * 4));
+    HR_TRY(h->short_n.ensure((size_t)nb * 4));
+    HR_TRY(h->tprime.ensure((size_t)nb * 4));
+    HR_TRY(h->flagged.ensure((size_t)nb * 4));
+    HR_TRY(h->counters.ensure(16));
+    HR_CUDA(cudaMemsetAsync(h->tau_g.p, 0, (size_t)nb * 4, st));
+    HR_CUDA(cudaMemsetAsync(h->counters.p, 0, 16, st));
+    CUtensorMap tq, tx;
+    const void* qsrc = h->storage == HR_STORAGE_F32 ? (const void*)h->qpad.p : (const void*)h->qh.p;
+    HR_TRY(make_tmap(&tq, qsrc, nb, h->ld, h->elem, kScanBM));
+    HR_TRY(make_tmap(&tx, h->x, h->ntotal, h->ld, h->elem, kScanBN));
+    ScanParams p;
+    p.N = h->ntotal;
+    p.nq = nb;
+    p.kblocks = (int)(row_bytes(h) / 128);
+    p.KL = KL;
+    p.num_ctiles = num_ctiles;
+    p.num_qtiles = (nb + kScanBM - 1) / kScanBM;
+    p.norms = h->norms;
+    p.lists = h->lists.as<Cand>();
+    p.cnts = h->cnts.as<int>();
+    p.tau_g = h->tau_g.as<unsigned int>();
+    cudaEventRecord(h->ev[2], st);
+    if (h->storage == HR_STORAGE_F32) {
+      if (h->metric == HR_METRIC_INNER_PRODUCT) HR_TRY((launch_scan<0, 0>(h, tq, tx, p, grid, st)));
+      else HR_TRY((launch_scan<0, 1>(h, tq, tx, p, grid, st)));
+    } else {
+      if (h->metric == HR_METRIC_INNER_PRODUCT) HR_TRY((launch_scan<1, 0>(h, tq, tx, p, grid, st)));
+      else HR_TRY((launch_scan<1, 1>(h, tq, tx, p, grid, st)));
+    }
+    cudaEventRecord(h->ev[3], st);
+    scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), grid,
+                                          nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
+                                          h->tprime.as<float>(), h->counters.as<int>() + 1);
+    HR_LAUNCHED();
+    // worst-case relative error of the filter score: both operands lose <= 2^-10 (tf32 truncation) or the
+    // query loses <= 2^-9 (bf16 rounding; bf16 rows are exact), plus fp32 accumulation over d terms
+    const float c_rel = 1.96e-3f + 2.4e-7f * (float)h->ld;
+    if (h->storage == HR_STORAGE_F32) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_rel, Db, Ib, st));
+    else HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_rel, Db, Ib, st));
+    HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 8, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) scan_ms_total += ms;
+    const int nflag = h->h_counters[0];
+    h->stats.flagged += nflag;
+    h->stats.overflow += h->h_counters[1];
+    if (nflag > 0) {
+      if (h->storage == HR_STORAGE_F32) HR_TRY(launch_exact<float>(h, h->flagged.as<int>(), nflag, k, Db, Ib, st));
+      else HR_TRY(launch_exact<__nv_bfloat16>(h, h->flagged.as<int>(), nflag, k, Db, Ib, st));
+    }
+  }
+  cudaEventRecord(h->ev[1], st);
+  HR_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->stats.total_ms = ms;
+  h->stats.scan_ms = scan_ms_total;
+  h->stats.launches = g_launches.load() - launches0;
+  return HR_OK;
+}
+
+extern "C" int hr_index_search(hr_index* h, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                               int io_on_device, void* stream) {
+  if (!h) return set_err(HR_ERR_INVALID, "null index");
+  if (nq < 0) return set_err(HR_ERR_INVALID, "nq < 0");
+  if (k <= 0 || k > HR_MAX_K) return set_err(HR_ERR_INVALID, "k must be in [1, 2048]");
+  if (nq == 0) return HR_OK;
+  if (!q || !D || !I) return set_err(HR_ERR_INVALID, "null q / D / I");
+  HR_DEVICE(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (io_on_device) return index_search_dev(h, q, nq, k, D, I, st);
+  HR_TRY(h->io_q.ensure((size_t)nq * h->d * 4));
+  HR_TRY(h->io_D.ensure((size_t)nq * k * 4));
+  HR_TRY(h->io_I.ensure((size_t)nq * k * 8));
+  HR_CUDA(cudaMemcpyAsync(h->io_q.p, q, (size_t)nq * h->d * 4, cudaMemcpyHostToDevice, st));
+  HR_TRY(index_search_dev(h, h->io_q.as<float>(), nq, k, h->io_D.as<float>(), h->io_I.as<int64_t>(), st));
+  HR_CUDA(cudaMemcpyAsync(D, h->io_D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+  HR_CUDA(cudaMemcpyAsync(I, h->io_I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+  HR_CUDA(cudaStreamSynchronize(st));
+  return HR_OK;
+}
+
+// ---- persistence: faiss flat-index bytes -----------------------------
+extern "C" int hr_index_save(hr_index* h, const char* path) {
+  if (!h || !path) return set_err(HR_ERR_INVALID, "null argument");
+  FILE* f = fopen(path, "wb");
+  if (!f) return set_err(HR_ERR_IO, std::string("cannot open for writing: ") + path);
+  const char* fourcc = h->metric == HR_METRIC_INNER_PRODUCT ? "IxFI" : "IxF2";
+  int32_t d = h->d, metric = h->metric;
+  int64_t nt = h->ntotal, dummy = 1 << 20;
+  uint8_t trained = 1;
+  uint64_t count = (uint64_t)h->ntotal * h->d;
+  bool ok = fwrite(fourcc, 1, 4, f) == 4 && fwrite(&d, 4, 1, f) == 1 && fwrite(&nt, 8, 1, f) == 1 &&
+            fwrite(&dummy, 8, 1, f) == 1 && fwrite(&dummy, 8, 1, f) == 1 && fwrite(&trained, 1, 1, f) == 1 &&
+            fwrite(&metric, 4, 1, f) == 1 && fwrite(&count, 8, 1, f) == 1;
+  const int64_t chunk = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->d * 4));
+  std::vector<float> buf;
+  for (int64_t r0 = 0; ok && r0 < h->ntotal; r0 += chunk) {
+    const int64_t nr = std::min(chunk, h->ntotal - r0);
+    buf.resize((size_t)nr * h->d);
+    int rc = hr_index_reconstruct(h, r0, nr, buf.data());
+    if (rc != HR_OK) {
+      fclose(f);
+      return rc;
+    }
+    ok = fwrite(buf.data(), 4, buf.size(), f) == buf.size();
+  }
+  if (fclose(f) != 0) ok = false;
+  if (!ok) return set_err(HR_ERR_IO, std::string("write failed: ") + path);
+  return HR_OK;
+}
+
+extern "C" int hr_index_load(const char* path, int device, int storage_dtype, hr_index** out) {
+  if (!path || !out) return set_err(HR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return set_err(HR_ERR_IO, std::string("cannot open index file: ") + path);
+  char fourcc[4];
+  int32_t d = 0, metric = 0;
+  int64_t nt = 0, dummy = 0;
+  uint8_t trained = 0;
+  uint64_t count = 0;
+  bool ok = fread(fourcc, 1, 4, f) == 4 && fread(&d, 4, 1, f) == 1 && fread(&nt, 8, 1, f) == 1 &&
+            fread(&dummy, 8, 1, f) == 1 && fread(&dummy, 8, 1, f) == 1 && fread(&trained, 1, 1, f) == 1 &&
+            fread(&metric, 4, 1, f) == 1;
+  if (ok && metric > 1) {
+    float arg;
+    ok = fread(&arg, 4, 1, f) == 1;
+  }
+  ok = ok && fread(&count, 8, 1, f) == 1;
+  const bool known = !memcmp(fourcc, "IxF2", 4) || !memcmp(fourcc, "IxFI", 4) || !memcmp(fourcc, "IxFl", 4);
+  if (!ok || !known || d <= 0 || nt < 0 || count != (uint64_t)nt * (uint64_t)d || metric < 0 || metric > 1) {
+    fclose(f);
+    return set_err(HR_ERR_IO, std::string("not a faiss flat index (IxF2/IxFI) or corrupt header: ") + path);
+  }
+  hr_index* h = nullptr;
+  int rc = hr_index_create(d, metric, storage_dtype, device, &h);
+  if (rc != HR_OK) {
+    fclose(f);
+    return rc;
+  }
+  rc = hr_index_reserve(h, nt);
+  const int64_t chunk = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)d * 4));
+  std::vector<float> buf;
+  for (int64_t r0 = 0; rc == HR_OK && r0 < nt; r0 += chunk) {
+    const int64_t nr = std::min(chunk, nt - r0);
+    buf.resize((size_t)nr * d);
+    if (fread(buf.data(), 4, buf.size(), f) != buf.size()) {
+      rc = set_err(HR_ERR_IO, std::string("truncated index file: ") + path);
+      break;
+    }
+    rc = hr_index_add(h, buf.data(), nr, 0, nullptr);
+  }
+  fclose(f);
+  if (rc != HR_OK) {
+    std::string keep = g_err;
+    hr_index_destroy(h);
+    g_err = keep;
+    return rc;
+  }
+  *out = h;
+  return HR_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// BM25
+// -------------------------------------------------------------------------------------------------
+struct hr_bm25 {
+  int device = 0;
+  int num_sms = 148;
+  int64_t N = 0, V = 0, nnz = 0, id_base = 0;
+  int64_t* indptr = nullptr;
+  int32_t* post_doc = nullptr;
+  float* post_imp = nullptr;
+  float* idf = nullptr;
+  DevBuf keys, ns, io_qi, io_qt, io_S, io_I, touched;
+};
+
+extern "C" int hr_bm25_destroy(hr_bm25* h) {
+  if (!h) return HR_OK;
+  DeviceGuard g(h->device);
+  if (h->indptr) cudaFree(h->indptr);
+  if (h->post_doc) cudaFree(h->post_doc);
+  if (h->post_imp) cudaFree(h->post_imp);
+  if (h->idf) cudaFree(h->idf);
+  DevBuf* bufs[] = {&h->keys, &h->ns, &h->io_qi, &h->io_qt, &h->io_S, &h->io_I, &h->touched};
+  for (DevBuf* b : bufs) b->release();
+  delete h;
+  return HR_OK;
+}
+extern "C" int64_t hr_bm25_ndocs(const hr_bm25* h) { return h ? h->N : -1; }
+extern "C" int64_t hr_bm25_vocab(const hr_bm25* h) { return h ? h->V : -1; }
+extern "C" int64_t hr_bm25_nnz(const hr_bm25* h) { return h ? h->nnz : -1; }
+extern "C" int hr_bm25_set_id_base(hr_bm25* h, int64_t id_base) {
+  if (!h) return set_err(HR_ERR_INVALID, "null bm25");
+  h->id_base = id_base;
+  return HR_OK;
+}
+
+extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
+                              const int32_t* doc_len, int64_t n_docs, int64_t vocab, float k1, float b,
+                              int idf_variant, int64_t n_docs_global, double avgdl_global,
+                              const int64_t* df_global, int is_device, int device, void* stream, hr_bm25** out) {
+  if (!out) return set_err(HR_ERR_INVALID, "null out");
+  *out = nullptr;
+  if (!indptr || n_docs < 0 || vocab <= 0) return set_err(HR_ERR_INVALID, "bad BM25 index arguments");
+  if (n_docs >= (int64_t)0x7FFFFFF0ll) return set_err(HR_ERR_INVALID, "too many docs for one shard");
+  if (idf_variant != HR_IDF_LUCENE && idf_variant != HR_IDF_OKAPI) return set_err(HR_ERR_INVALID, "idf variant");
+  int ndev = 0;
+  HR_TRY(hr_device_count(&ndev));
+  if (ndev <= 0) return set_err(HR_ERR_CUDA, "no CUDA device (hr_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(HR_ERR_INVALID, "device ordinal out of range");
+  HR_DEVICE(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  // host copy of indptr (df, nnz)
+  std::vector<int64_t> h_indptr((size_t)vocab + 1);
+  if (is_device) {
+    HR_CUDA(cudaMemcpyAsync(h_indptr.data(), indptr, (size_t)(vocab + 1) * 8, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(cudaStreamSynchronize(st));
+  } else {
+    memcpy(h_indptr.data(), indptr, (size_t)(vocab + 1) * 8);
+  }
+  const int64_t nnz = h_indptr[vocab];
+  if (h_indptr[0] != 0 || nnz < 0) return set_err(HR_ERR_INVALID, "indptr must start at 0 and be non-decreasing");
+  if (nnz > 0 && (!post_doc || !post_tf || !doc_len)) return set_err(HR_ERR_INVALID, "null postings");
+  std::vector<int64_t> h_df;
+  if (df_global) {
+    h_df.resize((size_t)vocab);
+    if (is_device) {
+      HR_CUDA(cudaMemcpyAsync(h_df.data(), df_global, (size_t)vocab * 8, cudaMemcpyDeviceToHost, st));
+      HR_CUDA(cudaStreamSynchronize(st));
+    } else {
+      memcpy(h_df.data(), df_global, (size_t)vocab * 8);
+    }
+  }
+  const double Ng = (double)(n_docs_global > 0 ? n_docs_global : n_docs);
+  std::vector<float> h_idf((size_t)vocab);
+  {
+    std::vector<double> raw((size_t)vocab);
+    double sum = 0.0;
+    int64_t present = 0;
+    for (int64_t t = 0; t < vocab; ++t) {
+      const double df = (double)(df_global ? h_df[t] : (h_indptr[t + 1] - h_indptr[t]));
+      if (idf_variant == HR_IDF_LUCENE) raw[t] = std::log((Ng - df + 0.5) / (df + 0.5) + 1.0);
+      else {
+        raw[t] = std::log((Ng - df + 0.5) / (df + 0.5));
+        if (df > 0) { sum += raw[t]; present++; }
+      }
+    }
+    const double eps = present ? 0.25 * (sum / (double)present) : 0.0;
+    for (int64_t t = 0; t < vocab; ++t) {
+      double v = raw[t];
+      if (idf_variant == HR_IDF_OKAPI && v < 0) v = eps;
+      h_idf[t] = (float)v;
+    }
+  }
+  hr_bm25* h = new hr_bm25();
+  h->device = device;
+  h->N = n_docs;
+  h->V = vocab;
+  h->nnz = nnz;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  int32_t* d_tf = nullptr;
+  int32_t* d_dl = nullptr;
+  auto fail = [&](int code, const char* msg) {
+    (void)cudaGetLastError();
+    if (d_tf) cudaFree(d_tf);
+    if (d_dl) cudaFree(d_dl);
+    hr_bm25_destroy(h);
+    return set_err(code, msg);
+  };
+  const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+  const size_t nd = (size_t)std::max<int64_t>(n_docs, 1);
+  if (cudaMalloc((void**)&h->indptr, (size_t)(vocab + 1) * 8) != cudaSuccess ||
+      cudaMalloc((void**)&h->post_doc, nz * 4) != cudaSuccess ||
+      cudaMalloc((void**)&h->post_imp, nz * 4) != cudaSuccess || cudaMalloc((void**)&h->idf, (size_t)vocab * 4) != cudaSuccess)
+    return fail(HR_ERR_NOMEM, "cudaMalloc failed for the BM25 index");
+  double avgdl = avgdl_global;
+  if (cudaMemcpyAsync(h->indptr, h_indptr.data(), (size_t)(vocab + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(h->idf, h_idf.data(), (size_t)vocab * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return fail(HR_ERR_CUDA, "copy of BM25 tables failed");
+  if (nnz > 0) {
+    if (cudaMemcpyAsync(h->post_doc, post_doc, (size_t)nnz * 4, kind, st) != cudaSuccess)
+      return fail(HR_ERR_CUDA, "copy of postings failed");
+    const int32_t* tfp = post_tf;
+    const int32_t* dlp = doc_len;
+    if (!is_device) {
+      if (cudaMalloc((void**)&d_tf, (size_t)nnz * 4) != cudaSuccess || cudaMalloc((void**)&d_dl, nd * 4) != cudaSuccess)
+        return fail(HR_ERR_NOMEM, "cudaMalloc failed for BM25 build scratch");
+      if (cudaMemcpyAsync(d_tf, post_tf, (size_t)nnz * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaMemcpyAsync(d_dl, doc_len, (size_t)n_docs * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return fail(HR_ERR_CUDA, "copy of BM25 build inputs failed");
+      tfp = d_tf;
+      dlp = d_dl;
+    }
+    if (!(avgdl > 0.0)) {
+      // local average document length (fp64 on the host, like the oracle)
+      std::vector<int32_t> h_dl((size_t)n_docs);
+      if (cudaMemcpyAsync(h_dl.data(), dlp, (size_t)n_docs * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)
+        return fail(HR_ERR_CUDA, "copy of doc_len failed");
+      double s = 0.0;
+      for (int64_t i = 0; i < n_docs; ++i) s += (double)h_dl[i];
+      avgdl = n_docs ? s / (double)n_docs : 0.0;
+    }
+    const int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)h->num_sms * 16);
+    bm25_impact_kernel<<<blocks, 256, 0, st>>>(h->post_doc, tfp, dlp, nnz, (double)k1, (double)b, avgdl, h->post_imp);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) return fail(HR_ERR_CUDA, "bm25_impact_kernel launch failed");
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(HR_ERR_CUDA, "BM25 build failed");
+  if (d_tf) cudaFree(d_tf);
+  if (d_dl) cudaFree(d_dl);
+  d_tf = d_dl = nullptr;
+  *out = h;
+  return HR_OK;
+}
+
+// device-pointer search; does not synchronise
+static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_dev, int64_t nq, int k, float* S_dev,
+                           int64_t* I_dev, cudaStream_t st, unsigned long long* touched_dev) {
+  if (nq == 0) return HR_OK;
+  if (k > kFuseMaxKc && k > 1024) return set_err(HR_ERR_INVALID, "bm25 k too large");
+  const int64_t NR = std::max<int64_t>(1, (h->N + kBmRange - 1) / kBmRange);
+  HR_CUDA(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmSmemBytes));
+  for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
+    const int nb = (int)std::min<int64_t>(32768, nq - q0);
+    int S = (int)((3 * 2 * (int64_t)h->num_sms + nb - 1) / nb);
+    S = std::min(S, (int)std::min<int64_t>(NR, 1 << 20));
+    S = std::max(1, std::min(S, std::max(1, kBmMergeCap / k)));
+    HR_TRY(h->keys.ensure((size_t)nb * S * k * 8));
+    HR_TRY(h->ns.ensure((size_t)nb * S * 4));
+    dim3 grid(S, nb);
+    bm25_score_kernel<<<grid, kBmThreads, kBmSmemBytes, st>>>(h->indptr, h->post_doc, h->post_imp, h->idf, h->N, h->V,
+                                                             qi_dev + q0, qt_dev, S, k, h->keys.as<uint64_t>(),
+                                                             h->ns.as<int>(), touched_dev);
+    HR_LAUNCHED();
+    bm25_merge_kernel<<<nb, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), S, k, k, h->id_base,
+                                          S_dev + q0 * k, I_dev + q0 * k);
+    HR_LAUNCHED();
+  }
+  return HR_OK;
+}
+
+extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t* q_terms, int64_t nq, int k,
+                              float* S, int64_t* I, int io_on_device, void* stream, int64_t* postings_touched) {
+  if (!h) return set_err(HR_ERR_INVALID, "null bm25");
+  if (nq < 0) return set_err(HR_ERR_INVALID, "nq < 0");
+  if (k <= 0 || k > 1024) return set_err(HR_ERR_INVALID, "bm25 k must be in [1, 1024]");
+  if (nq == 0) return HR_OK;
+  if (!q_indptr || !S || !I) return set_err(HR_ERR_INVALID, "null argument");
+  HR_DEVICE(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  HR_TRY(h->touched.ensure(8));
+  HR_CUDA(cudaMemsetAsync(h->touched.p, 0, 8, st));
+  if (io_on_device) {
+    HR_TRY(bm25_search_dev(h, q_indptr, q_terms, nq, k, S, I, st, h->touched.as<unsigned long long>()));
+  } else {
+    const int64_t nterms = q_indptr[nq];
+    for (int64_t i = 0; i < nq; ++i) {
+      if (q_indptr[i + 1] < q_indptr[i]) return set_err(HR_ERR_INVALID, "q_indptr must be non-decreasing");
+      if (q_indptr[i + 1] - q_indptr[i] > kBmMaxTerms)
+        return set_err(HR_ERR_INVALID, "a query has more than 256 terms");
+    }
+    HR_TRY(h->io_qi.ensure((size_t)(nq + 1) * 4));
+    HR_TRY(h->io_qt.ensure((size_t)std::max<int64_t>(nterms, 1) * 4));
+    HR_TRY(h->io_S.ensure((size_t)nq * k * 4));
+    HR_TRY(h->io_I.ensure((size_t)nq * k * 8));
+    HR_CUDA(cudaMemcpyAsync(h->io_qi.p, q_indptr, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (nterms > 0) HR_CUDA(cudaMemcpyAsync(h->io_qt.p, q_terms, (size_t)nterms * 4, cudaMemcpyHostToDevice, st));
+    HR_TRY(bm25_search_dev(h, h->io_qi.as<int32_t>(), h->io_qt.as<int32_t>(), nq, k, h->io_S.as<float>(),
+                           h->io_I.as<int64_t>(), st, h->touched.as<unsigned long long>()));
+    HR_CUDA(cudaMemcpyAsync(S, h->io_S.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(cudaMemcpyAsync(I, h->io_I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+  }
+  unsigned long long t = 0;
+  HR_CUDA(cudaMemcpyAsync(&t, h->touched.p, 8, cudaMemcpyDeviceToHost, st));
+  HR_CUDA(cudaStreamSynchronize(st));
+  if (postings_touched) *postings_touched = (int64_t)t;
+  return HR_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// fusion / merge
+// -------------------------------------------------------------------------------------------------
+extern "C" int hr_merge_topk(const float* S, const int64_t* I, int64_t nq, int n_cand, int k, int largest,
+                             float pad_score, float* out_S, int64_t* out_I, int device, void* stream) {
+  if (nq < 0 || n_cand <= 0 || k <= 0) return set_err(HR_ERR_INVALID, "bad merge arguments");
+  if (n_cand > kMergeTopkCap) return set_err(HR_ERR_INVALID, "merge: more than 2048 candidates per query");
+  if (nq == 0) return HR_OK;
+  if (!S || !I || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
+  HR_DEVICE(device);
+  merge_topk_kernel<<<(unsigned)nq, 256, 0, (cudaStream_t)stream>>>(S, I, n_cand, k, largest, pad_score, out_S, out_I);
+  HR_LAUNCHED();
+  return HR_OK;
+}
+
+extern "C" int hr_fuse(const float* dense_D, const int64_t* dense_I, const float* bm25_S, const int64_t* bm25_I,
+                       const float* bm25_max, int64_t nq, int kc, int top_k, int metric, int mode, float w_vec,
+                       float w_bm25, float* out_S, int64_t* out_I, int device, void* stream) {
+  if (nq < 0 || kc <= 0 || top_k <= 0) return set_err(HR_ERR_INVALID, "bad fuse arguments");
+  if (kc > kFuseMaxKc) return set_err(HR_ERR_INVALID, "fuse: candidate depth kc must be <= 256");
+  if (mode != HR_FUSE_WEIGHTED && mode != HR_FUSE_RRF) return set_err(HR_ERR_INVALID, "unknown fusion mode");
+  if (nq == 0) return HR_OK;
+  if (!dense_D || !dense_I || !bm25_S || !bm25_I || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
+  HR_DEVICE(device);
+  fuse_kernel<<<(unsigned)nq, 256, 0, (cudaStream_t)stream>>>(dense_D, dense_I, bm25_S, bm25_I, bm25_max, kc, top_k,
+                                                             metric, mode, w_vec, w_bm25, out_S, out_I);
+  HR_LAUNCHED();
+  return HR_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// whole hot path on one device
+// -------------------------------------------------------------------------------------------------
+
+extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
+                           const int32_t* q_terms, int64_t nq, int top_k, int kc, int mode, float w_vec,
+                           float w_bm25, float* out_S, int64_t* out_I, int io_on_device, void* stream) {
+  if (!ix) return set_err(HR_ERR_INVALID, "null index");
+  if (nq < 0 || top_k <= 0) return set_err(HR_ERR_INVALID, "bad retrieve arguments");
+  if (kc <= 0) kc = top_k > 50 ? top_k : 50;  // live path depth, rag/query/page_retriever.py:81
+  if (kc < top_k) kc = top_k;
+  if (kc > kFuseMaxKc) return set_err(HR_ERR_INVALID, "retrieve: candidate depth must be <= 256");
+  if (nq == 0) return HR_OK;
+  if (!q || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
+  if (bm && (!q_indptr)) return set_err(HR_ERR_INVALID, "null query tokens");
+  if (bm && bm->device != ix->device) return set_err(HR_ERR_INVALID, "index and bm25 live on different devices");
+  HR_DEVICE(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  RetrieveScratch& rs = ix->rs;
+  HR_TRY(rs.dD.ensure((size_t)nq * kc * 4));
+  HR_TRY(rs.dI.ensure((size_t)nq * kc * 8));
+  HR_TRY(rs.bS.ensure((size_t)nq * kc * 4));
+  HR_TRY(rs.bI.ensure((size_t)nq * kc * 8));
+  const float* qd = q;
+  const int32_t* qid = q_indptr;
+  const int32_t* qtd = q_terms;
+  float* oS = out_S;
+  int64_t* oI = out_I;
+  if (!io_on_device) {
+    HR_TRY(rs.q.ensure((size_t)nq * ix->d * 4));
+    HR_CUDA(cudaMemcpyAsync(rs.q.p, q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
+    qd = rs.q.as<float>();
+    if (bm) {
+      const int64_t nterms = q_indptr[nq];
+      for (int64_t i = 0; i < nq; ++i)
+        if (q_indptr[i + 1] < q_indptr[i] || q_indptr[i + 1] - q_indptr[i] > kBmMaxTerms)
+          return set_err(HR_ERR_INVALID, "bad q_indptr (non-monotone, or a query has more than 256 terms)");
+      HR_TRY(rs.qi.ensure((size_t)(nq + 1) * 4));
+      HR_TRY(rs.qt.ensure((size_t)std::max<int64_t>(nterms, 1) * 4));
+      HR_CUDA(cudaMemcpyAsync(rs.qi.p, q_indptr, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, st));
+      if (nterms > 0) HR_CUDA(cudaMemcpyAsync(rs.qt.p, q_terms, (size_t)nterms * 4, cudaMemcpyHostToDevice, st));
+      qid = rs.qi.as<int32_t>();
+      qtd = rs.qt.as<int32_t>();
+    }
+    HR_TRY(rs.oS.ensure((size_t)nq * top_k * 4));
+    HR_TRY(rs.oI.ensure((size_t)nq * top_k * 8));
+    oS = rs.oS.as<float>();
+    oI = rs.oI.as<int64_t>();
+  }
+  // BM25 first (asynchronous), then the dense search (which synchronises), then fusion
+  if (bm) {
+    HR_TRY(bm25_search_dev(bm, qid, qtd, nq, kc, rs.bS.as<float>(), rs.bI.as<int64_t>(), st, nullptr));
+  } else {
+    fill_pad_kernel<<<(int)std::min<int64_t>((nq * kc + 255) / 256, 1024), 256, 0, st>>>(
+        rs.bS.as<float>(), rs.bI.as<int64_t>(), nq * kc, 0.f);
+    HR_LAUNCHED();
+  }
+  HR_TRY(index_search_dev(ix, qd, nq, kc, rs.dD.as<float>(), rs.dI.as<int64_t>(), st));
+  fuse_kernel<<<(unsigned)nq, 256, 0, st>>>(rs.dD.as<float>(), rs.dI.as<int64_t>(), rs.bS.as<float>(),
+                                            rs.bI.as<int64_t>(), nullptr, kc, top_k, ix->metric, mode, w_vec, w_bm25,
+                                            oS, oI);
+  HR_LAUNCHED();
+  if (!io_on_device) {
+    HR_CUDA(cudaMemcpyAsync(out_S, oS, (size_t)nq * top_k * 4, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(cudaMemcpyAsync(out_I, oI, (size_t)nq * top_k * 8, cudaMemcpyDeviceToHost, st));
+  }
+  HR_CUDA(cudaStreamSynchronize(st));
+  return HR_OK;
+}

@@ -1,0 +1,171 @@
+"""Host-side mirror of the reference's storage wrapper, backed by the B200 flat index.
+
+Same function names, arguments and error behaviour as /root/reference/rag/storage/faiss_index.py
+(FAISSIndexReader :26-103, create_faiss_index :106-128, save_faiss_index :131-134,
+search_faiss_by_vector :137-199, initialize_storage :202-228) so the service code calls it
+unchanged.  Written against this package's :mod:`.faiss`; nothing is copied from the reference.
+
+Deliberate, documented deviations:
+  * padded hits (id -1, when limit > ntotal) are dropped instead of silently mapping to the LAST
+    chunk through Python's negative indexing (faiss_index.py:180-181);
+  * the index cache is keyed by (path, mtime) so a re-ingested document is seen without restart;
+  * the chunk JSON is parsed once per (path, mtime) instead of once per query (faiss_index.py:175).
+"""
+from __future__ import annotations
+
+import glob
+import json
+import logging
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import faiss
+from .config import config
+
+logger = logging.getLogger("intool_rag_b200.storage")
+
+_INDEX_CACHE: Dict[Tuple[str, float], "faiss.Index"] = {}
+_CHUNK_CACHE: Dict[Tuple[str, float], List[dict]] = {}
+
+
+def _mtime(path: str) -> float:
+    try:
+        return os.path.getmtime(path)
+    except OSError:
+        return -1.0
+
+
+class FAISSIndexReader:
+    """Read-only index wrapper with caching (reference: faiss_index.py:26-103)."""
+
+    def __init__(self, index_path: str):
+        self.index_path = str(index_path)
+        self.index = None
+        self._load_index()
+
+    def _load_index(self) -> None:
+        key = (self.index_path, _mtime(self.index_path))
+        hit = _INDEX_CACHE.get(key)
+        if hit is not None:
+            self.index = hit
+            return
+        try:
+            self.index = faiss.read_index(self.index_path)
+        except Exception as e:  # same wrapping as the reference (:60-61)
+            raise RuntimeError(f"Failed to load FAISS index: {e}")
+        for old in [k for k in _INDEX_CACHE if k[0] == self.index_path]:
+            del _INDEX_CACHE[old]
+        _INDEX_CACHE[key] = self.index
+        logger.info("Loaded FAISS index: %s (d=%d, %d vectors)", self.index_path, self.index.d, self.index.ntotal)
+
+    def search(self, query_embedding: List[float], top_k: int = 10) -> List[Tuple[int, float]]:
+        """[(row id, score)], score = clamp(1 - squared_L2 / 2, 0, 1) — the reference transform
+        (:86-88), evaluated in Python floats on the fp32 distance exactly as the reference does."""
+        if self.index is None:
+            raise RuntimeError("Index not loaded")
+        q = np.array([query_embedding], dtype=np.float32)
+        D, I = self.index.search(q, top_k)
+        out = []
+        for idx, dist in zip(I[0], D[0]):
+            score = 1.0 - (float(dist) / 2.0)
+            score = max(0.0, min(1.0, score))
+            out.append((int(idx), float(score)))
+        return out
+
+    def get_dimension(self) -> int:
+        if self.index is None:
+            raise RuntimeError("Index not loaded")
+        return self.index.d
+
+    def get_size(self) -> int:
+        if self.index is None:
+            raise RuntimeError("Index not loaded")
+        return self.index.ntotal
+
+
+def create_faiss_index(embeddings) -> "faiss.Index":
+    """Build an IndexFlatL2 from a list of vectors / ndarray (reference: faiss_index.py:106-128)."""
+    x = np.array(embeddings, dtype=np.float32)
+    if x.ndim != 2:
+        raise ValueError("embeddings must be a non-empty [n, d] array")
+    index = faiss.IndexFlatL2(x.shape[1])
+    index.add(x)
+    logger.info("Created FAISS index: %d vectors, dim=%d", index.ntotal, index.d)
+    return index
+
+
+def save_faiss_index(index: "faiss.Index", path: str) -> None:
+    faiss.write_index(index, path)
+    logger.info("Saved FAISS index to %s", path)
+
+
+def _load_chunk_list(storage_dir: str, doc_id: str) -> List[dict]:
+    path = os.path.join(storage_dir, f"{doc_id}_chunks.json")
+    key = (path, _mtime(path))
+    hit = _CHUNK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"Chunks not found: {path}")
+    with open(path, "r", encoding="utf-8") as f:
+        data = json.load(f)
+    by_id = {}
+    for c in data.get("chunks", []):  # the reference keys by chunk_id, then lists dict values
+        by_id[c["chunk_id"]] = c
+    chunks = list(by_id.values())
+    for old in [k for k in _CHUNK_CACHE if k[0] == path]:
+        del _CHUNK_CACHE[old]
+    _CHUNK_CACHE[key] = chunks
+    return chunks
+
+
+async def search_faiss_by_vector(query_vector: List[float], limit: int = 50,
+                                 project: Optional[str] = None) -> List[dict]:
+    """Search the first ``*_faiss.index`` under STORAGE_DIR and enrich hits with chunk metadata
+    (reference: faiss_index.py:137-199; `project` is accepted and ignored there too)."""
+    storage_dir = os.environ.get("STORAGE_DIR", config.STORAGE_DIR)
+    index_files = sorted(glob.glob(os.path.join(str(storage_dir), "*_faiss.index")))
+    if not index_files:
+        logger.warning("No FAISS indices found")
+        return []
+    index_path = index_files[0]
+    reader = FAISSIndexReader(index_path)
+    hits = reader.search(query_vector, top_k=limit)
+    doc_id = os.path.basename(index_path)[: -len(".index")].replace("_faiss", "")
+    chunks = _load_chunk_list(str(storage_dir), doc_id)
+    out = []
+    for row, score in hits:
+        if 0 <= row < len(chunks):
+            c = chunks[row]
+            meta = c.get("metadata", {})
+            out.append({
+                "chunk_id": c.get("chunk_id", f"unknown_{row}"),
+                "text": c.get("text", ""),
+                "score": score,
+                "page": c.get("page", 0),
+                "chapter": meta.get("chapter"),
+                "section": meta.get("section"),
+                "subsection": meta.get("subsection"),
+                "title": meta.get("title"),
+                "source_filename": meta.get("source_filename"),
+            })
+    logger.info("FAISS search returned %d results", len(out))
+    return out
+
+
+async def initialize_storage() -> None:
+    """Pre-load every ``*_faiss.index`` under STORAGE_DIR into HBM (reference: faiss_index.py:202-228)."""
+    storage_dir = os.environ.get("STORAGE_DIR", config.STORAGE_DIR)
+    if not os.path.isdir(str(storage_dir)):
+        logger.warning("Storage directory not found: %s", storage_dir)
+        return
+    count = 0
+    for path in sorted(glob.glob(os.path.join(str(storage_dir), "*_faiss.index"))):
+        try:
+            FAISSIndexReader(path)
+            count += 1
+        except Exception as e:
+            logger.error("Failed to pre-load index %s: %s", path, e)
+    logger.info("Initialized storage: loaded %d indices into HBM", count)

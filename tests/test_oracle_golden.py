@@ -1,0 +1,169 @@
+"""CPU: the oracle against the committed golden vectors (hand-computed KATs and the outputs of
+the reference's unmodified wrapper).  This is what pins the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flat, bm25, fusion, hybrid
+
+
+@pytest.fixture(scope="module")
+def kat_flat(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "kat_flat.json")))
+
+
+def test_flat_l2_kat(kat_flat):
+    ix = flat.IndexFlatL2(4)
+    ix.add(np.array(kat_flat["x"], np.float32))
+    D, I = ix.search(np.array(kat_flat["q"], np.float32), 7)
+    assert I.tolist() == kat_flat["l2_k7_ids"]
+    np.testing.assert_allclose(D, np.array(kat_flat["l2_k7_dist"], np.float32), atol=1e-6)
+    np.testing.assert_allclose(flat.reference_score_from_l2(D[0]), kat_flat["ref_score_q0"], atol=1e-6)
+
+
+def test_flat_ip_kat(kat_flat):
+    ix = flat.IndexFlatIP(4)
+    ix.add(np.array(kat_flat["x"], np.float32))
+    D, I = ix.search(np.array(kat_flat["q"], np.float32), 7)
+    assert I.tolist() == kat_flat["ip_k7_ids"]
+    np.testing.assert_allclose(D, np.array(kat_flat["ip_k7_score"], np.float32), atol=1e-6)
+
+
+def test_flat_padding_and_empty(kat_flat):
+    ix = flat.IndexFlatL2(4)
+    D, I = ix.search(np.zeros((2, 4), np.float32), 3)
+    assert (I == -1).all() and (D == flat.FLT_MAX).all()
+    ix.add(np.array(kat_flat["x"], np.float32))
+    D, I = ix.search(np.array(kat_flat["q"], np.float32)[:1], 9)
+    assert I[0].tolist() == kat_flat["k9_pad_ids_q0"]
+    assert (D[0, 7:] == flat.FLT_MAX).all()
+    ip = flat.IndexFlatIP(4)
+    ip.add(np.array(kat_flat["x"], np.float32)[:2])
+    D, I = ip.search(np.array(kat_flat["q"], np.float32)[:1], 4)
+    assert I[0].tolist() == [0, 1, -1, -1] and (D[0, 2:] == -flat.FLT_MAX).all()
+
+
+def test_l2_ip_rank_equivalence_on_unit_norm():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((400, 32)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = x[:7] + 0.05 * rng.standard_normal((7, 32)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    a, b = flat.IndexFlatL2(32), flat.IndexFlatIP(32)
+    a.add(x), b.add(x)
+    Dl, Il = a.search(q, 10, precision="f64")
+    Di, Ii = b.search(q, 10, precision="f64")
+    assert (Il == Ii).all()
+    np.testing.assert_allclose(1.0 - Dl / 2.0, Di, atol=5e-7)
+
+
+def test_f32_vs_f64_tolerance_budget():
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((2000, 256)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = x[:30]
+    ix = flat.IndexFlatIP(256)
+    ix.add(x)
+    assert np.abs(ix.scores_f32(q) - ix.scores_f64(q)).max() < 2e-6
+
+
+def test_index_file_roundtrip_and_reference_bytes(golden_dir, tmp_path):
+    z = np.load(os.path.join(golden_dir, "ref_wrapper.npz"))
+    g = json.load(open(os.path.join(golden_dir, "ref_wrapper.json")))
+    raw = z["index_bytes"].tobytes()
+    # header layout of Appendix A item 6 as produced through the reference's save_faiss_index
+    assert raw[:4] == b"IxF2" and len(raw) == 45 + g["n"] * g["d"] * 4 == g["index_nbytes"]
+    p = tmp_path / "a_faiss.index"
+    p.write_bytes(raw)
+    ix = flat.read_index(str(p))
+    assert (ix.d, ix.ntotal, ix.metric_type) == (g["d"], g["n"], flat.METRIC_L2)
+    np.testing.assert_array_equal(ix._x, z["x"])
+    p2 = tmp_path / "b_faiss.index"
+    flat.write_index(ix, str(p2))
+    assert p2.read_bytes() == raw
+
+
+def test_reference_wrapper_outputs_match_oracle_semantics(golden_dir):
+    """What the reference's FAISSIndexReader.search returned (run in the build container on the
+    oracle stand-in) equals oracle search + the reference transform, including -1 padding."""
+    z = np.load(os.path.join(golden_dir, "ref_wrapper.npz"))
+    g = json.load(open(os.path.join(golden_dir, "ref_wrapper.json")))
+    ix = flat.IndexFlatL2(g["d"])
+    ix.add(z["x"])
+    for qi, q in enumerate(z["queries"]):
+        for k in (1, 5, 10, 50):
+            D, I = ix.search(q[None, :], k)
+            want = g["reader_search"][f"q{qi}_k{k}"]
+            assert [w[0] for w in want] == I[0].tolist()
+            np.testing.assert_allclose([w[1] for w in want], flat.reference_score_from_l2(D[0]), atol=1e-7)
+    assert g["reader_search"]["q0_k5"][0][0] == 3 and g["reader_search"]["q0_k5"][1][0] == 5  # dup rows tie: id asc
+
+
+def test_bm25_kat(golden_dir):
+    k = json.load(open(os.path.join(golden_dir, "kat_bm25.json")))
+    c = bm25.BM25Corpus(k["docs"], k["vocab"], k1=k["k1"], b=k["b"])
+    for q, want in zip(k["queries"], k["scores"]):
+        np.testing.assert_allclose(c.scores(q), want, rtol=1e-12, atol=1e-12)
+    S, I = c.search(k["queries"], 3)
+    assert I[0].tolist() == [int(i) for i in np.lexsort((np.arange(3), -np.array(k["scores"][0])))]
+    assert I[1].tolist() == [2, 1, -1]        # doc 0 has score 0 -> not a candidate
+    assert I[2].tolist() == [-1, -1, -1] and (S[2] == 0).all()
+
+
+def test_bm25_okapi_floor():
+    idf = bm25.idf_table(np.array([1, 9, 0]), 10, "okapi")
+    raw = np.log((10 - np.array([1, 9]) + 0.5) / (np.array([1, 9]) + 0.5))
+    assert idf[0] == pytest.approx(raw[0]) and idf[1] == pytest.approx(0.25 * raw.mean())
+
+
+def test_fusion_kat(golden_dir):
+    k = json.load(open(os.path.join(golden_dir, "kat_fusion.json")))
+    args = (np.array(k["dense_sim"]), np.array(k["dense_ids"]), np.array(k["bm25"], np.float32), np.array(k["bm25_ids"]))
+    for mode in ("weighted", "rrf"):
+        S, I = fusion.fuse(*args, top_k=7, mode=mode, w_vec=k["w_vec"], w_bm25=k["w_bm25"])
+        assert I[0].tolist() == [t[0] for t in k[mode]]
+        np.testing.assert_allclose(S[0], [t[1] for t in k[mode]], rtol=1e-6)
+    S, I = fusion.fuse(*args, top_k=9, mode="weighted")
+    assert I[0, 7:].tolist() == [-1, -1] and (S[0, 7:] == 0).all()
+
+
+def test_merge_shards_equals_single_shard():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((300, 16)).astype(np.float32)
+    x[150] = x[20]
+    q = rng.standard_normal((9, 16)).astype(np.float32)
+    q[0] = x[20]
+    full = flat.IndexFlatIP(16)
+    full.add(x)
+    D, I = full.search(q, 12)
+    parts_S, parts_I = [], []
+    for lo, hi in ((0, 100), (100, 230), (230, 300)):
+        s = flat.IndexFlatIP(16)
+        s.add(x[lo:hi])
+        d, i = s.search(q, 12)
+        parts_S.append(d)
+        parts_I.append(np.where(i >= 0, i + lo, -1))
+    S, J = fusion.merge_shards(np.concatenate(parts_S, 1), np.concatenate(parts_I, 1), 12, largest=True)
+    assert (J == I).all() and np.array_equal(S, D)
+
+
+def test_synthetic_small_golden_is_reproducible(golden_dir):
+    """The committed fp64-oracle answers regenerate from the seeds (guards generator drift)."""
+    import intool_rag_b200  # noqa: F401
+    from intool_rag_b200 import synth
+    z = np.load(os.path.join(golden_dir, "synthetic_small.npz"))
+    n, d, V, nq = int(z["n"]), int(z["d"]), int(z["V"]), int(z["nq"])
+    x = synth.dense_corpus_np(n, d)
+    x[100] = x[7]
+    q = synth.dense_queries_np(x, nq)
+    ix = flat.IndexFlatIP(d)
+    ix.add(x)
+    D, I = ix.search(q, 50, precision="f64")
+    assert (I == z["ip_I"]).all()
+    t, dd, dl = synth.sparse_corpus_np(n, V, mean_len=40.0)
+    qt = synth.sparse_queries_np(nq, V, stop=8)
+    c = bm25.BM25Corpus.from_token_matrix(t, dd, dl, V)
+    fs, fi, _ = hybrid.retrieve(ix, c, q, qt, 10, precision="f64")
+    assert (fi == z["ip_weighted_I"]).all()
