@@ -92,14 +92,16 @@ __global__ void convert_pad_norm_kernel(const float* __restrict__ src, int64_t n
 }
 
 // queries fp32 [nq, d] -> padded fp32 [nq, ld] (+ optional bf16 copy for the bf16 filter)
-__global__ void pad_queries_kernel(const float* __restrict__ q, int64_t nq, int d, int ld, float* __restrict__ qp,
-                                   __nv_bfloat16* __restrict__ qh) {
+// rows [nq, nq_rows) are written as zeros: the TMA box of a small batch then still reads >= 32 distinct
+// cache lines per K block instead of every SM hammering the same line of a 1-row query matrix.
+__global__ void pad_queries_kernel(const float* __restrict__ q, int64_t nq, int64_t nq_rows, int d, int ld,
+                                   float* __restrict__ qp, __nv_bfloat16* __restrict__ qh) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = nq * (int64_t)ld;
+  int64_t total = nq_rows * (int64_t)ld;
   for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / ld;
     int c = (int)(i - r * ld);
-    float v = (c < d) ? q[r * (int64_t)d + c] : 0.f;
+    float v = (r < nq && c < d) ? q[r * (int64_t)d + c] : 0.f;
     qp[i] = v;
     if (qh) qh[i] = __float2bfloat16_rn(v);
   }

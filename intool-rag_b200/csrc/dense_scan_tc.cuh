@@ -54,7 +54,8 @@ struct ScanParams {
   int nq;           // queries in this launch (<= kScanNqMax)
   int kblocks;      // 128-byte K blocks per row (ld * elem_size / 128)
   int KL;           // candidate list length
-  int num_ctiles;   // ceil(N / 256)
+  int tile_count;   // corpus tiles this launch visits: tiles t*tile_stride, t in [0, tile_count)
+  int tile_stride;  // 1 = every tile (main pass), >1 = strided sample (threshold pre-pass)
   int num_qtiles;   // ceil(nq / 128)
   const float* norms;  // |x|^2 per row (L2 only)
   Cand* lists;         // [gridDim.x][nq][KL]
@@ -137,7 +138,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int c = blockIdx.x; c < p.num_ctiles; c += gridDim.x) {
+      for (int t = blockIdx.x; t < p.tile_count; t += gridDim.x) {
+        const int c = t * p.tile_stride;
         for (int m = 0; m < p.num_qtiles; ++m) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&st->empty_bar[stage], phase ^ 1);
@@ -159,7 +161,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (int c = blockIdx.x; c < p.num_ctiles; c += gridDim.x) {
+      for (int t = blockIdx.x; t < p.tile_count; t += gridDim.x) {
         for (int m = 0; m < p.num_qtiles; ++m, ++it) {
           const uint32_t as = it & 1u;
           const uint32_t aphase = (it >> 1) & 1u;
@@ -196,7 +198,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const int et = threadIdx.x - 128;
     uint32_t it = 0;
     uint32_t cit = 0;
-    for (int c = blockIdx.x; c < p.num_ctiles; c += gridDim.x, ++cit) {
+    for (int t = blockIdx.x; t < p.tile_count; t += gridDim.x, ++cit) {
+      const int c = t * p.tile_stride;
       const int nb = cit & 1;
       if (METRIC == 1) {
         for (int j = et; j < kScanBN; j += 128) {
@@ -282,39 +285,89 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // ---- merge of the per-CTA candidate lists -> shortlist for the exact re-score -------------------
 // One block per query.  Keeps entries with score >= T* (= final tau_g), sorts them by key, emits
 // the best KL rows and tprime = upper bound on the approximate score of everything left out.
+// When more than kShortCap entries survive T* (small corpora: few tiles per CTA, so the shared
+// threshold never tightens) an exact 4-pass radix select finds the KL-th largest score first.
 constexpr int kShortCap = 2048;
 
-__global__ void __launch_bounds__(256)
-scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
-                  const unsigned int* __restrict__ tau_g, int G, int nq, int KL,
-                  uint32_t* __restrict__ short_rows, int* __restrict__ short_n, float* __restrict__ tprime,
-                  int* __restrict__ overflow_count) {
-  __shared__ uint64_t buf[kShortCap];
-  __shared__ int s_n;
-  const int q = blockIdx.x;
-  const unsigned int o = tau_g[q];
-  const float tstar = o ? ord2f(o) : HR_NEG_INF;
-  if (threadIdx.x == 0) s_n = 0;
+__device__ __forceinline__ int merge_compact(const Cand* __restrict__ lists, const int* __restrict__ cnts, int G,
+                                             int nq, int KL, int q, float tstar, uint32_t ord_min, uint64_t* buf,
+                                             int* s_n) {
+  if (threadIdx.x == 0) *s_n = 0;
   __syncthreads();
   const int total = G * KL;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     int g = i / KL, j = i - g * KL;
     if (j < cnts[(size_t)g * nq + q]) {
       Cand c = lists[((size_t)g * nq + q) * KL + j];
-      if (c.s >= tstar) {
-        int slot = atomicAdd(&s_n, 1);
+      if (c.s >= tstar && f2ord(c.s) >= ord_min) {
+        int slot = atomicAdd(s_n, 1);
         if (slot < kShortCap) buf[slot] = make_key(c.s, c.row);
       }
     }
   }
   __syncthreads();
-  const int n = s_n;
+  return *s_n;
+}
+
+__global__ void __launch_bounds__(256)
+scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
+                  const unsigned int* __restrict__ tau_g, int G, int nq, int KL,
+                  uint32_t* __restrict__ short_rows, int* __restrict__ short_n, float* __restrict__ tprime,
+                  int* __restrict__ overflow_count, unsigned int* __restrict__ tau_seed) {
+  __shared__ uint64_t buf[kShortCap];
+  __shared__ int s_n;
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  const int q = blockIdx.x;
+  const unsigned int o = tau_g[q];
+  const float tstar = o ? ord2f(o) : HR_NEG_INF;
+  int n = merge_compact(lists, cnts, G, nq, KL, q, tstar, 0u, buf, &s_n);
+  bool radix = false;
+  if (n > kShortCap) {
+    // exact KL-th largest ordered score among the entries >= T*  (MSB-first radix select)
+    radix = true;
+    if (threadIdx.x == 0) {
+      s_prefix = 0;
+      s_remaining = KL;
+    }
+    const int total = G * KL;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+      __syncthreads();
+      const uint32_t mask = (shift == 24) ? 0u : (0xFFFFFFFFu << (shift + 8));
+      const uint32_t prefix = s_prefix;
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int g = i / KL, j = i - g * KL;
+        if (j < cnts[(size_t)g * nq + q]) {
+          float sc = lists[((size_t)g * nq + q) * KL + j].s;
+          uint32_t od = f2ord(sc);
+          if (sc >= tstar && (od & mask) == (prefix & mask)) atomicAdd(&hist[(od >> shift) & 255u], 1);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int cum = 0, rem = s_remaining;
+        for (int b = 255; b >= 0; --b) {
+          if (cum + hist[b] >= rem) {
+            s_prefix = prefix | ((uint32_t)b << shift);
+            s_remaining = rem - cum;
+            break;
+          }
+          cum += hist[b];
+        }
+      }
+      __syncthreads();
+    }
+    n = merge_compact(lists, cnts, G, nq, KL, q, tstar, s_prefix, buf, &s_n);
+  }
   uint32_t* out = short_rows + (size_t)q * KL;
-  if (n > kShortCap) {  // cannot rank: send the query to the exact fallback
+  if (n > kShortCap) {  // massive exact ties at the KL-th score: cannot rank -> exact fallback
     if (threadIdx.x == 0) {
       short_n[q] = 0;
       tprime[q] = -HR_NEG_INF;
-      atomicAdd(overflow_count, 1);
+      if (tau_seed) tau_seed[q] = o;
+      else atomicAdd(overflow_count, 1);
     }
     for (int j = threadIdx.x; j < KL; j += blockDim.x) out[j] = 0xFFFFFFFFu;
     return;
@@ -328,8 +381,12 @@ scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
     short_n[q] = n < KL ? n : KL;
     float tp = HR_NEG_INF;
     if (o) tp = tstar;                                  // rows dropped by a threshold are <= T*
-    if (n > KL) tp = fmaxf(tp, key_score(buf[KL]));     // best list entry that was left out
+    if (n > KL) tp = fmaxf(tp, key_score(buf[KL]));     // best compacted entry that was left out
+    else if (radix && n > 0) tp = fmaxf(tp, key_score(buf[n - 1]));  // entries below the radix threshold
     tprime[q] = tp;
+    // threshold pre-pass: the KL-th best score of the SAMPLE is a valid lower bound of the KL-th best
+    // of the whole corpus (the sample rows are corpus rows) -> seed of tau_g for the main pass
+    if (tau_seed) tau_seed[q] = (n >= KL) ? (uint32_t)(buf[KL - 1] >> 32) : o;
   }
 }
 

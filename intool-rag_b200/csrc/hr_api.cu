@@ -378,6 +378,8 @@ __global__ void iota_kernel(int* a, int n, int base) {
   if (i < n) a[i] = base + i;
 }
 
+constexpr int kSampleStride = 64;  // threshold pre-pass visits every 64th corpus tile
+
 static int list_len_for_k(int k) {
   if (k <= 16) return 32;
   if (k <= 32) return 64;
@@ -481,12 +483,13 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     const int nb = (int)std::min<int64_t>(kScanNqMax, nq - q0);
     float* Db = D_dev + q0 * k;
     int64_t* Ib = I_dev + q0 * k;
-    HR_TRY(h->qpad.ensure((size_t)nb * h->ld * 4));
-    if (h->storage == HR_STORAGE_BF16) HR_TRY(h->qh.ensure((size_t)nb * h->ld * 2));
+    const int nbp = std::max(nb, 32);  // query rows materialised for the TMA (zero rows beyond nb)
+    HR_TRY(h->qpad.ensure((size_t)nbp * h->ld * 4));
+    if (h->storage == HR_STORAGE_BF16) HR_TRY(h->qh.ensure((size_t)nbp * h->ld * 2));
     {
-      const int64_t tot = (int64_t)nb * h->ld;
+      const int64_t tot = (int64_t)nbp * h->ld;
       pad_queries_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 2048), 256, 0, st>>>(
-          q_dev + q0 * h->d, nb, h->d, h->ld, h->qpad.as<float>(),
+          q_dev + q0 * h->d, nb, nbp, h->d, h->ld, h->qpad.as<float>(),
           h->storage == HR_STORAGE_BF16 ? h->qh.as<__nv_bfloat16>() : nullptr);
       HR_LAUNCHED();
     }
@@ -511,31 +514,47 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     HR_CUDA(cudaMemsetAsync(h->counters.p, 0, 16, st));
     CUtensorMap tq, tx;
     const void* qsrc = h->storage == HR_STORAGE_F32 ? (const void*)h->qpad.p : (const void*)h->qh.p;
-    HR_TRY(make_tmap(&tq, qsrc, nb, h->ld, h->elem, kScanBM));
+    HR_TRY(make_tmap(&tq, qsrc, nbp, h->ld, h->elem, kScanBM));
     HR_TRY(make_tmap(&tx, h->x, h->ntotal, h->ld, h->elem, kScanBN));
     ScanParams p;
     p.N = h->ntotal;
     p.nq = nb;
     p.kblocks = (int)(row_bytes(h) / 128);
     p.KL = KL;
-    p.num_ctiles = num_ctiles;
     p.num_qtiles = (nb + kScanBM - 1) / kScanBM;
     p.norms = h->norms;
     p.lists = h->lists.as<Cand>();
     p.cnts = h->cnts.as<int>();
     p.tau_g = h->tau_g.as<unsigned int>();
-    cudaEventRecord(h->ev[2], st);
-    if (h->storage == HR_STORAGE_F32) {
-      if (h->metric == HR_METRIC_INNER_PRODUCT) HR_TRY((launch_scan<0, 0>(h, tq, tx, p, grid, st)));
-      else HR_TRY((launch_scan<0, 1>(h, tq, tx, p, grid, st)));
-    } else {
-      if (h->metric == HR_METRIC_INNER_PRODUCT) HR_TRY((launch_scan<1, 0>(h, tq, tx, p, grid, st)));
-      else HR_TRY((launch_scan<1, 1>(h, tq, tx, p, grid, st)));
+    auto run_scan = [&](int g) -> int {
+      if (h->storage == HR_STORAGE_F32) {
+        if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<0, 0>(h, tq, tx, p, g, st);
+        return launch_scan<0, 1>(h, tq, tx, p, g, st);
+      }
+      if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<1, 0>(h, tq, tx, p, g, st);
+      return launch_scan<1, 1>(h, tq, tx, p, g, st);
+    };
+    // ---- threshold pre-pass over a strided 1/64 sample of the corpus tiles: its exact top-KL gives
+    //      every query a threshold that is already tight when the main pass starts ----
+    if (num_ctiles >= kSampleStride * 16) {
+      p.tile_stride = kSampleStride;
+      p.tile_count = (num_ctiles + kSampleStride - 1) / kSampleStride;
+      const int gs = std::min(p.tile_count, h->num_sms);
+      HR_TRY(run_scan(gs));
+      scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), gs,
+                                            nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
+                                            h->tprime.as<float>(), h->counters.as<int>() + 1,
+                                            h->tau_g.as<unsigned int>());
+      HR_LAUNCHED();
     }
+    p.tile_stride = 1;
+    p.tile_count = num_ctiles;
+    cudaEventRecord(h->ev[2], st);
+    HR_TRY(run_scan(grid));
     cudaEventRecord(h->ev[3], st);
     scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), grid,
                                           nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
-                                          h->tprime.as<float>(), h->counters.as<int>() + 1);
+                                          h->tprime.as<float>(), h->counters.as<int>() + 1, nullptr);
     HR_LAUNCHED();
     // worst-case relative error of the filter score: both operands lose <= 2^-10 (tf32 truncation) or the
     // query loses <= 2^-9 (bf16 rounding; bf16 rows are exact), plus fp32 accumulation over d terms
@@ -826,20 +845,24 @@ extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, co
 static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_dev, int64_t nq, int k, float* S_dev,
                            int64_t* I_dev, cudaStream_t st, unsigned long long* touched_dev) {
   if (nq == 0) return HR_OK;
-  if (k > kFuseMaxKc && k > 1024) return set_err(HR_ERR_INVALID, "bm25 k too large");
-  const int64_t NR = std::max<int64_t>(1, (h->N + kBmRange - 1) / kBmRange);
-  HR_CUDA(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmSmemBytes));
+  if (k > kBmMaxK) return set_err(HR_ERR_INVALID, "bm25: k must be <= 128");
+  int kcp = 32;
+  while (kcp < k) kcp <<= 1;
+  const int smem = bm_smem_bytes(kcp);
+  const int64_t nwin = std::max<int64_t>(1, (h->N + kBmWin - 1) / kBmWin);
+  HR_CUDA(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
     const int nb = (int)std::min<int64_t>(32768, nq - q0);
-    int S = (int)((3 * 2 * (int64_t)h->num_sms + nb - 1) / nb);
-    S = std::min(S, (int)std::min<int64_t>(NR, 1 << 20));
+    // enough CTAs for ~4 per SM; a CTA needs at least one window per warp to be worth launching
+    int S = (int)((4 * (int64_t)h->num_sms + nb - 1) / nb);
+    S = (int)std::min<int64_t>(S, std::max<int64_t>(1, nwin / kBmWarps));
     S = std::max(1, std::min(S, std::max(1, kBmMergeCap / k)));
     HR_TRY(h->keys.ensure((size_t)nb * S * k * 8));
     HR_TRY(h->ns.ensure((size_t)nb * S * 4));
     dim3 grid(S, nb);
-    bm25_score_kernel<<<grid, kBmThreads, kBmSmemBytes, st>>>(h->indptr, h->post_doc, h->post_imp, h->idf, h->N, h->V,
-                                                             qi_dev + q0, qt_dev, S, k, h->keys.as<uint64_t>(),
-                                                             h->ns.as<int>(), touched_dev);
+    bm25_score_kernel<<<grid, kBmThreads, smem, st>>>(h->indptr, h->post_doc, h->post_imp, h->idf, h->N, h->V,
+                                                     qi_dev + q0, qt_dev, S, k, kcp, h->keys.as<uint64_t>(),
+                                                     h->ns.as<int>(), touched_dev);
     HR_LAUNCHED();
     bm25_merge_kernel<<<nb, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), S, k, k, h->id_base,
                                           S_dev + q0 * k, I_dev + q0 * k);
@@ -852,7 +875,7 @@ extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t
                               float* S, int64_t* I, int io_on_device, void* stream, int64_t* postings_touched) {
   if (!h) return set_err(HR_ERR_INVALID, "null bm25");
   if (nq < 0) return set_err(HR_ERR_INVALID, "nq < 0");
-  if (k <= 0 || k > 1024) return set_err(HR_ERR_INVALID, "bm25 k must be in [1, 1024]");
+  if (k <= 0 || k > kBmMaxK) return set_err(HR_ERR_INVALID, "bm25 k must be in [1, 128]");
   if (nq == 0) return HR_OK;
   if (!q_indptr || !S || !I) return set_err(HR_ERR_INVALID, "null argument");
   HR_DEVICE(h->device);
@@ -866,7 +889,7 @@ extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t
     for (int64_t i = 0; i < nq; ++i) {
       if (q_indptr[i + 1] < q_indptr[i]) return set_err(HR_ERR_INVALID, "q_indptr must be non-decreasing");
       if (q_indptr[i + 1] - q_indptr[i] > kBmMaxTerms)
-        return set_err(HR_ERR_INVALID, "a query has more than 256 terms");
+        return set_err(HR_ERR_INVALID, "a query has more than 64 terms");
     }
     HR_TRY(h->io_qi.ensure((size_t)(nq + 1) * 4));
     HR_TRY(h->io_qt.ensure((size_t)std::max<int64_t>(nterms, 1) * 4));
@@ -927,7 +950,7 @@ extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int3
   if (nq < 0 || top_k <= 0) return set_err(HR_ERR_INVALID, "bad retrieve arguments");
   if (kc <= 0) kc = top_k > 50 ? top_k : 50;  // live path depth, rag/query/page_retriever.py:81
   if (kc < top_k) kc = top_k;
-  if (kc > kFuseMaxKc) return set_err(HR_ERR_INVALID, "retrieve: candidate depth must be <= 256");
+  if (kc > kBmMaxK) return set_err(HR_ERR_INVALID, "retrieve: candidate depth must be <= 128");
   if (nq == 0) return HR_OK;
   if (!q || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
   if (bm && (!q_indptr)) return set_err(HR_ERR_INVALID, "null query tokens");
@@ -952,7 +975,7 @@ extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int3
       const int64_t nterms = q_indptr[nq];
       for (int64_t i = 0; i < nq; ++i)
         if (q_indptr[i + 1] < q_indptr[i] || q_indptr[i + 1] - q_indptr[i] > kBmMaxTerms)
-          return set_err(HR_ERR_INVALID, "bad q_indptr (non-monotone, or a query has more than 256 terms)");
+          return set_err(HR_ERR_INVALID, "bad q_indptr (non-monotone, or a query has more than 64 terms)");
       HR_TRY(rs.qi.ensure((size_t)(nq + 1) * 4));
       HR_TRY(rs.qt.ensure((size_t)std::max<int64_t>(nterms, 1) * 4));
       HR_CUDA(cudaMemcpyAsync(rs.qi.p, q_indptr, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, st));

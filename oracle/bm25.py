@@ -66,6 +66,29 @@ class BM25Corpus:
                          np.asarray(doc_len, np.int64))
         return self
 
+    @classmethod
+    def from_csr(cls, indptr, post_doc, post_tf, doc_len, vocab_size: int, k1: float = K1, b: float = B,
+                 idf_variant: str = "lucene", n_docs_global: int = 0, avgdl_global: float = 0.0,
+                 df_global=None) -> "BM25Corpus":
+        """Wrap ready CSR arrays (optionally a row shard scored with corpus-wide statistics)."""
+        self = cls.__new__(cls)
+        self.N = int(len(doc_len))
+        self.V = int(vocab_size)
+        self.k1, self.b, self.idf_variant = float(k1), float(b), idf_variant
+        self.indptr = np.asarray(indptr, np.int64)
+        self.post_doc = np.asarray(post_doc, np.int32)
+        self.post_tf = np.asarray(post_tf, np.int32)
+        self.doc_len = np.asarray(doc_len, np.int32)
+        self.avgdl = float(avgdl_global) if avgdl_global > 0 else (
+            float(self.doc_len.astype(np.float64).mean()) if self.N else 0.0)
+        self.df = np.diff(self.indptr).astype(np.int64) if df_global is None else np.asarray(df_global, np.int64)
+        self.idf = idf_table(self.df, int(n_docs_global) if n_docs_global > 0 else self.N, idf_variant)
+        dl = self.doc_len[self.post_doc].astype(np.float64)
+        tf64 = self.post_tf.astype(np.float64)
+        norm = self.k1 * (1.0 - self.b + self.b * dl / self.avgdl) if self.avgdl > 0 else self.k1
+        self.impact = tf64 * (self.k1 + 1.0) / (tf64 + norm)
+        return self
+
     def _from_pairs(self, t: np.ndarray, dd: np.ndarray, doc_len: np.ndarray) -> None:
         N, V = self.N, self.V
         self.doc_len = doc_len.astype(np.int32)
