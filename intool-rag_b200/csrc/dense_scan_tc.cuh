@@ -90,6 +90,62 @@ __device__ __noinline__ void cand_insert(Cand* list, int KL, float v, uint32_t r
   thr = fmaxf(m, tg);
 }
 
+// One (corpus tile, query tile) accumulator: thread = query q (TMEM lane), 256 columns = corpus rows.
+// Reads the accumulator in 32-column chunks and feeds scores above the query's threshold to its list.
+template <int METRIC>
+__device__ __forceinline__ void scan_epilogue_item(ScanSmemTail* st, const ScanParams& p, uint32_t taddr, int q, int nb,
+                                                   int col_limit, uint32_t row0) {
+        const bool active = q < p.nq;
+        float tau_l = HR_NEG_INF, tg = HR_NEG_INF, thr = HR_NEG_INF;
+        uint32_t cnt = 0, minpos = 0;
+        Cand* list = nullptr;
+        if (active) {
+          tau_l = st->tau_l[q];
+          cnt = st->cnt[q];
+          minpos = st->minpos[q];
+          unsigned int o = *((volatile unsigned int*)&p.tau_g[q]);
+          tg = o ? ord2f(o) : HR_NEG_INF;
+          thr = (cnt == (uint32_t)p.KL) ? fmaxf(tau_l, tg) : tg;
+          list = p.lists + ((size_t)blockIdx.x * p.nq + q) * p.KL;
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < kScanBN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          if (active) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __uint_as_float(r[j]);
+              if (METRIC == 1) v[j] -= st->half_norms[nb][ch * 32 + j];
+            }
+            const int cbase = ch * 32;
+            if (cbase + 32 <= col_limit) {
+              float mx = v[0];
+#pragma unroll
+              for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+              if (mx > thr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (v[j] > thr)
+                    cand_insert(list, p.KL, v[j], row0 + cbase + j, tau_l, cnt, minpos, thr, tg, &p.tau_g[q]);
+              }
+            } else if (cbase < col_limit) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < col_limit && v[j] > thr)
+                  cand_insert(list, p.KL, v[j], row0 + cbase + j, tau_l, cnt, minpos, thr, tg, &p.tau_g[q]);
+            }
+          }
+        }
+        if (active) {
+          st->tau_l[q] = tau_l;
+          st->cnt[q] = (uint16_t)cnt;
+          st->minpos[q] = (uint16_t)minpos;
+        }
+}
+
 // KIND 0: fp32 storage, kind::tf32 (32 elements per K block).  KIND 1: bf16 storage, kind::f16.
 template <int KIND, int METRIC>
 __global__ void __launch_bounds__(kScanThreads, 1)
@@ -215,60 +271,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const uint32_t as = it & 1u;
         const uint32_t aphase = (it >> 1) & 1u;
         const int q = m * kScanBM + ew * 32 + lane;
-        const bool active = q < p.nq;
-        float tau_l = HR_NEG_INF, tg = HR_NEG_INF, thr = HR_NEG_INF;
-        uint32_t cnt = 0, minpos = 0;
-        Cand* list = nullptr;
-        if (active) {
-          tau_l = st->tau_l[q];
-          cnt = st->cnt[q];
-          minpos = st->minpos[q];
-          unsigned int o = *((volatile unsigned int*)&p.tau_g[q]);
-          tg = o ? ord2f(o) : HR_NEG_INF;
-          thr = (cnt == (uint32_t)p.KL) ? fmaxf(tau_l, tg) : tg;
-          list = p.lists + ((size_t)blockIdx.x * p.nq + q) * p.KL;
-        }
         mbar_wait(&st->tmem_full[as], aphase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16);
-#pragma unroll 1
-        for (int ch = 0; ch < kScanBN / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch * 32, r);
-          tmem_ld_wait();
-          if (active) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(r[j]);
-              if (METRIC == 1) v[j] -= st->half_norms[nb][ch * 32 + j];
-            }
-            const int cbase = ch * 32;
-            if (cbase + 32 <= col_limit) {
-              float mx = v[0];
-#pragma unroll
-              for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-              if (mx > thr) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (v[j] > thr)
-                    cand_insert(list, p.KL, v[j], row0 + cbase + j, tau_l, cnt, minpos, thr, tg, &p.tau_g[q]);
-              }
-            } else if (cbase < col_limit) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cbase + j < col_limit && v[j] > thr)
-                  cand_insert(list, p.KL, v[j], row0 + cbase + j, tau_l, cnt, minpos, thr, tg, &p.tau_g[q]);
-            }
-          }
-        }
+        scan_epilogue_item<METRIC>(st, p, tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16), q, nb, col_limit,
+                                   row0);
         tc_fence_before();
         mbar_arrive(&st->tmem_empty[as]);
-        if (active) {
-          st->tau_l[q] = tau_l;
-          st->cnt[q] = (uint16_t)cnt;
-          st->minpos[q] = (uint16_t)minpos;
-        }
       }
     }
     for (int q = et; q < p.nq; q += 128) p.cnts[(size_t)blockIdx.x * p.nq + q] = st->cnt[q];
@@ -279,6 +287,179 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) for batches of more than 128 queries.
+//   One MMA spans two SMs: M = 256 queries (CTA r of the pair owns queries [r*128, r*128+128) of the
+//   256-query pair tile and their accumulators in its own TMEM), N = 256 corpus rows of which each CTA
+//   stages only its half (128 rows) in shared memory.  Per SM and K block that is 16 KB of queries +
+//   16 KB of corpus for 128x256x32 MACs: 2/3 of the single-CTA kernel's operand traffic, and only one
+//   1 MB corpus tile in flight per PAIR, so the tiles of all pairs (74 MB) stay L2 resident while the
+//   pair sweeps its query tiles over them.
+//   Barriers: TMA of both CTAs completes on the LEADER's full barrier; the leader's MMA thread commits
+//   (multicast) to both CTAs' empty / tmem_full barriers; both epilogues arrive on the leader's tmem_empty.
+// =====================================================================================================
+constexpr int kScan2Stages = 6;
+constexpr int kScan2HalfBytes = 128 * 128;                 // 128 rows x 128 B
+constexpr int kScan2StageBytes = 2 * kScan2HalfBytes;      // A half + B half
+constexpr int kScan2SmemBytes = kScan2Stages * kScan2StageBytes + (int)sizeof(ScanSmemTail) + 1024;
+static_assert(kScan2Stages <= 8, "barrier arrays");
+
+struct Scan2Bars {
+  uint64_t full_bar[kScan2Stages];
+  uint64_t empty_bar[kScan2Stages];
+};
+
+template <int KIND, int METRIC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kScanThreads, 1)
+scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  ScanSmemTail* st = (ScanSmemTail*)(smem + kScan2Stages * kScan2StageBytes);
+  __shared__ Scan2Bars bars;
+  constexpr int kKElems = (KIND == 0) ? 32 : 64;
+  constexpr uint32_t kIdesc = umma_idesc(KIND == 0 ? 2u : 1u, 256, kScanBN);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int num_ptiles = (p.nq + 255) / 256;   // 256-query pair tiles
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kScan2Stages; ++s) {
+      mbar_init(&bars.full_bar[s], 1);
+      mbar_init(&bars.empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&st->tmem_full[a], 1);
+      mbar_init(&st->tmem_empty[a], 256);   // 128 epilogue threads of each CTA
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(&st->tmem_ptr, 512);
+    tmem_relinquish2();
+  }
+  for (int i = threadIdx.x; i < kScanNqMax; i += blockDim.x) {
+    st->tau_l[i] = HR_NEG_INF;
+    st->cnt[i] = 0;
+    st->minpos[i] = 0;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = st->tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < p.tile_count; t += npairs) {
+        const int c = t * p.tile_stride;
+        for (int m = 0; m < num_ptiles; ++m) {
+          // the corpus tile is re-read by the following query tiles: keep it in L2 until the last one
+          const uint64_t xpol = (m == num_ptiles - 1) ? kEvictFirst : kEvictLast;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&bars.empty_bar[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&bars.full_bar[stage], 2 * kScan2StageBytes);
+            uint8_t* sa = smem + stage * kScan2StageBytes;
+            tma_load_2d_pair(sa, &tmap_q, &bars.full_bar[stage], kb * kKElems, m * 256 + (int)rank * 128,
+                             kEvictLast);
+            tma_load_2d_pair(sa + kScan2HalfBytes, &tmap_x, &bars.full_bar[stage], kb * kKElems,
+                             c * kScanBN + (int)rank * 128, xpol);
+            if (++stage == kScan2Stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int t = pair; t < p.tile_count; t += npairs) {
+        for (int m = 0; m < num_ptiles; ++m, ++it) {
+          const uint32_t as = it & 1u;
+          const uint32_t aphase = (it >> 1) & 1u;
+          mbar_wait(&st->tmem_empty[as], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * kScanBN;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&bars.full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kScan2StageBytes);
+            const uint64_t adesc = umma_desc_sw128(sa);
+            const uint64_t bdesc = umma_desc_sw128(sa + kScan2HalfBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (KIND == 0)
+                tc_mma2_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (uint32_t)((kb | k) != 0));
+              else
+                tc_mma2_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (uint32_t)((kb | k) != 0));
+            }
+            tc_commit2(&bars.empty_bar[stage]);
+            if (++stage == kScan2Stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit2(&st->tmem_full[as]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs; CTA r owns queries r*128.. of each pair tile) =========
+    const int ew = warp & 3;
+    const int et = threadIdx.x - 128;
+    uint32_t it = 0;
+    uint32_t cit = 0;
+    for (int t = pair; t < p.tile_count; t += npairs, ++cit) {
+      const int c = t * p.tile_stride;
+      const int nb = cit & 1;
+      if (METRIC == 1) {
+        for (int j = et; j < kScanBN; j += 128) {
+          int64_t row = (int64_t)c * kScanBN + j;
+          st->half_norms[nb][j] = row < p.N ? 0.5f * p.norms[row] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const int64_t rem = p.N - (int64_t)c * kScanBN;
+      const int col_limit = rem < kScanBN ? (int)rem : kScanBN;
+      const uint32_t row0 = (uint32_t)c * kScanBN;
+      for (int m = 0; m < num_ptiles; ++m, ++it) {
+        const uint32_t as = it & 1u;
+        const uint32_t aphase = (it >> 1) & 1u;
+        const int q = m * 256 + (int)rank * 128 + ew * 32 + lane;
+        mbar_wait(&st->tmem_full[as], aphase);
+        tc_fence_after();
+        scan_epilogue_item<METRIC>(st, p, tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16), q, nb, col_limit,
+                                   row0);
+        tc_fence_before();
+        mbar_arrive_leader(&st->tmem_empty[as]);
+      }
+    }
+    for (int q = et; q < p.nq; q += 128) p.cnts[(size_t)blockIdx.x * p.nq + q] = st->cnt[q];
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still touch this CTA
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -438,6 +439,16 @@ static int launch_scan(hr_index* h, const CUtensorMap& tq, const CUtensorMap& tx
   return HR_OK;
 }
 
+template <int KIND, int METRIC>
+static int launch_scan2(hr_index* h, const CUtensorMap& tq, const CUtensorMap& tx, const ScanParams& p, int grid,
+                        cudaStream_t st) {
+  HR_CUDA(cudaFuncSetAttribute(scan_tc2_kernel<KIND, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kScan2SmemBytes));
+  scan_tc2_kernel<KIND, METRIC><<<grid, kScanThreads, kScan2SmemBytes, st>>>(tq, tx, p);
+  HR_LAUNCHED();
+  return HR_OK;
+}
+
 template <typename T>
 static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_rel, float* D, int64_t* I, cudaStream_t st) {
   const size_t smem = (size_t)KL * 8;
@@ -502,8 +513,8 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
       continue;
     }
     // ---- tensor-core filter scan ----
-    HR_TRY(h->lists.ensure((size_t)grid * nb * KL * sizeof(Cand)));
-    HR_TRY(h->cnts.ensure((size_t)grid * nb * 4));
+    HR_TRY(h->lists.ensure((size_t)h->num_sms * nb * KL * sizeof(Cand)));
+    HR_TRY(h->cnts.ensure((size_t)h->num_sms * nb * 4));
     HR_TRY(h->tau_g.ensure((size_t)nb * 4));
     HR_TRY(h->short_rows.ensure((size_t)nb * KL * 4));
     HR_TRY(h->short_n.ensure((size_t)nb * 4));
@@ -526,7 +537,20 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     p.lists = h->lists.as<Cand>();
     p.cnts = h->cnts.as<int>();
     p.tau_g = h->tau_g.as<unsigned int>();
+    // batches of more than 128 queries run on CTA pairs (cta_group::2, 128-row corpus halves per CTA)
+    const bool use_pair = nb > kScanBM && h->num_sms >= 2 && !getenv("HR_NO_PAIR");
+    CUtensorMap tx2;
+    if (use_pair) HR_TRY(make_tmap(&tx2, h->x, h->ntotal, h->ld, h->elem, 128));
     auto run_scan = [&](int g) -> int {
+      if (use_pair) {
+        const int g2 = std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1);
+        if (h->storage == HR_STORAGE_F32) {
+          if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan2<0, 0>(h, tq, tx2, p, g2, st);
+          return launch_scan2<0, 1>(h, tq, tx2, p, g2, st);
+        }
+        if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan2<1, 0>(h, tq, tx2, p, g2, st);
+        return launch_scan2<1, 1>(h, tq, tx2, p, g2, st);
+      }
       if (h->storage == HR_STORAGE_F32) {
         if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<0, 0>(h, tq, tx, p, g, st);
         return launch_scan<0, 1>(h, tq, tx, p, g, st);
@@ -534,25 +558,34 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
       if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<1, 0>(h, tq, tx, p, g, st);
       return launch_scan<1, 1>(h, tq, tx, p, g, st);
     };
-    // ---- threshold pre-pass over a strided 1/64 sample of the corpus tiles: its exact top-KL gives
-    //      every query a threshold that is already tight when the main pass starts ----
-    if (num_ctiles >= kSampleStride * 16) {
-      p.tile_stride = kSampleStride;
-      p.tile_count = (num_ctiles + kSampleStride - 1) / kSampleStride;
-      const int gs = std::min(p.tile_count, h->num_sms);
+    // ---- threshold pre-pass over a strided sample of the corpus tiles.  The sample's KLs-th best score
+    //      seeds tau_g: about KLs*stride (= 4*KL) corpus rows beat it, so in the main pass only a handful
+    //      of scores per CTA pass the threshold and no per-CTA list ever fills.  Correctness never depends
+    //      on the seed: the certificate in rescore_finalize compares against the final threshold. ----
+    const int stride = std::max(1, std::min(kSampleStride, num_ctiles / 8));
+    if (stride > 1) {
+      const int KLs = std::max(8, std::min(KL, (4 * KL + stride - 1) / stride));
+      p.KL = KLs;
+      p.tile_stride = stride;
+      p.tile_count = (num_ctiles + stride - 1) / stride;
+      const int gs = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1)
+                              : std::min(p.tile_count, h->num_sms);
       HR_TRY(run_scan(gs));
       scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), gs,
-                                            nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
+                                            nb, KLs, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
                                             h->tprime.as<float>(), h->counters.as<int>() + 1,
                                             h->tau_g.as<unsigned int>());
       HR_LAUNCHED();
+      p.KL = KL;
     }
     p.tile_stride = 1;
     p.tile_count = num_ctiles;
     cudaEventRecord(h->ev[2], st);
-    HR_TRY(run_scan(grid));
+    const int gmain = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1) : grid;
+    HR_TRY(run_scan(gmain));
     cudaEventRecord(h->ev[3], st);
-    scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), grid,
+    h->stats.grid = gmain;
+    scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), gmain,
                                           nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
                                           h->tprime.as<float>(), h->counters.as<int>() + 1, nullptr);
     HR_LAUNCHED();
