@@ -127,11 +127,13 @@ int64_t hr_bm25_ndocs(const hr_bm25* h);
 int64_t hr_bm25_vocab(const hr_bm25* h);
 int64_t hr_bm25_nnz(const hr_bm25* h);
 int hr_bm25_set_id_base(hr_bm25* h, int64_t id_base);
-/* queries as CSR: q_indptr int32[nq+1], q_terms int32[q_indptr[nq]] (duplicates count, ids
- * outside [0,V) ignored).  S float32[nq,k] descending, I int64[nq,k], padding I=-1,S=0.
- * postings_touched (optional, host int64) receives the number of postings scored. */
+/* queries as CSR: q_indptr int32[nq+1], q_terms int32[n_terms] with n_terms >= q_indptr[nq]
+ * (duplicates count, ids outside [0,V) ignored, at most 64 terms per query).  n_terms < 0 = unknown
+ * (device io then reads q_indptr[nq] back, one small synchronous copy).  S float32[nq,k]
+ * descending, I int64[nq,k], padding I=-1,S=0.  postings_touched (optional, host int64)
+ * receives the number of postings scored. */
 int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t* q_terms, int64_t nq,
-                   int k, float* S, int64_t* I, int io_on_device, void* stream,
+                   int64_t n_terms, int k, float* S, int64_t* I, int io_on_device, void* stream,
                    int64_t* postings_touched);
 
 /* ---- fusion + merges (all pointers are DEVICE pointers, ordered on `stream`) ----------- */
@@ -151,7 +153,7 @@ int hr_fuse(const float* dense_D, const int64_t* dense_I, const float* bm25_S,
  * retrieve(query_embeddings, query_tokens, top_k) of rag/query/retriever.py (path
  * advertised at README.md:90).  bm may be NULL (dense only).  Host or device io. */
 int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
-                const int32_t* q_terms, int64_t nq, int top_k, int kc, int mode, float w_vec,
+                const int32_t* q_terms, int64_t nq, int64_t n_terms, int top_k, int kc, int mode, float w_vec,
                 float w_bm25, float* out_S, int64_t* out_I, int io_on_device, void* stream);
 
 #ifdef __cplusplus

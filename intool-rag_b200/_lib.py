@@ -58,11 +58,11 @@ SYMBOLS = {
     "hr_bm25_vocab": (C.c_int64, [_p]),
     "hr_bm25_nnz": (C.c_int64, [_p]),
     "hr_bm25_set_id_base": (C.c_int, [_p, C.c_int64]),
-    "hr_bm25_search": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int, _p, _p, C.c_int, _p, C.POINTER(C.c_int64)]),
+    "hr_bm25_search": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int, _p, _p, C.c_int, _p, C.POINTER(C.c_int64)]),
     "hr_merge_topk": (C.c_int, [_p, _p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _p, _p, C.c_int, _p]),
     "hr_fuse": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                           C.c_float, _p, _p, C.c_int, _p]),
-    "hr_retrieve": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+    "hr_retrieve": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                               _p, _p, C.c_int, _p]),
 }
 

@@ -182,14 +182,15 @@ class BM25Index:
             nq = int(indptr.shape[0]) - 1
             S = torch.empty((nq, k), dtype=torch.float32, device=indptr.device)
             I = torch.empty((nq, k), dtype=torch.int64, device=indptr.device)
-            _lib.check(_lib.lib().hr_bm25_search(self._h, indptr.data_ptr(), terms.data_ptr(), nq, k, S.data_ptr(),
+            _lib.check(_lib.lib().hr_bm25_search(self._h, indptr.data_ptr(), terms.data_ptr(), nq, int(terms.numel()), k,
+                                                 S.data_ptr(),
                                                  I.data_ptr(), 1, _lib.current_stream_ptr(self.device),
                                                  C.byref(touched)))
         else:
             nq = len(indptr) - 1
             S = np.empty((nq, k), dtype=np.float32)
             I = np.empty((nq, k), dtype=np.int64)
-            _lib.check(_lib.lib().hr_bm25_search(self._h, indptr.ctypes.data, terms.ctypes.data, nq, k,
+            _lib.check(_lib.lib().hr_bm25_search(self._h, indptr.ctypes.data, terms.ctypes.data, nq, int(terms.size), k,
                                                  S.ctypes.data, I.ctypes.data, 0,
                                                  _lib.current_stream_ptr(self.device), C.byref(touched)))
         if return_postings:

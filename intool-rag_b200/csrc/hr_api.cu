@@ -729,7 +729,7 @@ struct hr_bm25 {
   int32_t* post_doc = nullptr;
   float* post_imp = nullptr;
   float* idf = nullptr;
-  DevBuf keys, ns, io_qi, io_qt, io_S, io_I, touched;
+  DevBuf keys, ns, io_qi, io_qt, io_S, io_I, touched, plan_nt, plan_start, plan_len, plan_wgt, plan_cur, tau;
 };
 
 extern "C" int hr_bm25_destroy(hr_bm25* h) {
@@ -739,7 +739,8 @@ extern "C" int hr_bm25_destroy(hr_bm25* h) {
   if (h->post_doc) cudaFree(h->post_doc);
   if (h->post_imp) cudaFree(h->post_imp);
   if (h->idf) cudaFree(h->idf);
-  DevBuf* bufs[] = {&h->keys, &h->ns, &h->io_qi, &h->io_qt, &h->io_S, &h->io_I, &h->touched};
+  DevBuf* bufs[] = {&h->keys,    &h->ns,         &h->io_qi,    &h->io_qt,    &h->io_S,     &h->io_I, &h->touched,
+                    &h->plan_nt, &h->plan_start, &h->plan_len, &h->plan_wgt, &h->plan_cur, &h->tau};
   for (DevBuf* b : bufs) b->release();
   delete h;
   return HR_OK;
@@ -874,38 +875,70 @@ extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, co
   return HR_OK;
 }
 
-// device-pointer search; does not synchronise
-static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_dev, int64_t nq, int k, float* S_dev,
-                           int64_t* I_dev, cudaStream_t st, unsigned long long* touched_dev) {
+// device-pointer search; does not synchronise.  n_terms = length of q_terms (sizes the plan).
+static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_dev, int64_t nq, int64_t n_terms,
+                           int k, float* S_dev, int64_t* I_dev, cudaStream_t st, unsigned long long* touched_dev) {
   if (nq == 0) return HR_OK;
   if (k > kBmMaxK) return set_err(HR_ERR_INVALID, "bm25: k must be <= 128");
+  if (nq >= (int64_t)0x7FFFFFF0ll) return set_err(HR_ERR_INVALID, "bm25: too many queries in one call");
+  if (n_terms < 0) {  // unknown to the caller: read q_indptr[nq] back (one small synchronous copy)
+    int32_t last = 0;
+    HR_CUDA(cudaMemcpyAsync(&last, qi_dev + nq, 4, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(cudaStreamSynchronize(st));
+    n_terms = last;
+  }
   int kcp = 32;
   while (kcp < k) kcp <<= 1;
-  const int smem = bm_smem_bytes(kcp);
-  const int64_t nwin = std::max<int64_t>(1, (h->N + kBmWin - 1) / kBmWin);
-  HR_CUDA(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  for (int64_t q0 = 0; q0 < nq; q0 += 32768) {
-    const int nb = (int)std::min<int64_t>(32768, nq - q0);
-    // enough CTAs for ~4 per SM; a CTA needs at least one window per warp to be worth launching
-    int S = (int)((4 * (int64_t)h->num_sms + nb - 1) / nb);
-    S = (int)std::min<int64_t>(S, std::max<int64_t>(1, nwin / kBmWarps));
-    S = std::max(1, std::min(S, std::max(1, kBmMergeCap / k)));
-    HR_TRY(h->keys.ensure((size_t)nb * S * k * 8));
-    HR_TRY(h->ns.ensure((size_t)nb * S * 4));
-    dim3 grid(S, nb);
-    bm25_score_kernel<<<grid, kBmThreads, smem, st>>>(h->indptr, h->post_doc, h->post_imp, h->idf, h->N, h->V,
-                                                     qi_dev + q0, qt_dev, S, k, kcp, h->keys.as<uint64_t>(),
-                                                     h->ns.as<int>(), touched_dev);
-    HR_LAUNCHED();
-    bm25_merge_kernel<<<nb, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), S, k, k, h->id_base,
-                                          S_dev + q0 * k, I_dev + q0 * k);
+  const int smem = bw_smem_bytes(kcp);
+  const int64_t nwin = std::max<int64_t>(1, (h->N + kBwWin - 1) / kBwWin);
+  const size_t cur_bytes = (size_t)std::max<int64_t>(n_terms, 1) * (size_t)(nwin + 1) * 4;
+  if (cur_bytes > ((size_t)8 << 30))
+    return set_err(HR_ERR_INVALID, "bm25: query batch too large for the cursor table (split the batch)");
+  // spans per query: ~6 waves of CTAs over the machine (3 resident per SM), bounded by the merge capacity
+  int64_t S = (6 * 3 * (int64_t)h->num_sms + nq - 1) / nq;
+  S = std::max<int64_t>(1, std::min<int64_t>({S, nwin, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
+  const int wpc = (int)((nwin + S - 1) / S);
+  S = (nwin + wpc - 1) / wpc;
+  const size_t nterm_slots = (size_t)std::max<int64_t>(n_terms, 1);
+  HR_TRY(h->plan_nt.ensure((size_t)nq * 4));
+  HR_TRY(h->plan_start.ensure(nterm_slots * 8));
+  HR_TRY(h->plan_len.ensure(nterm_slots * 4));
+  HR_TRY(h->plan_wgt.ensure(nterm_slots * 4));
+  HR_TRY(h->plan_cur.ensure(cur_bytes));
+  HR_TRY(h->tau.ensure((size_t)nq * 8));
+  HR_TRY(h->keys.ensure((size_t)nq * S * k * 8));
+  HR_TRY(h->ns.ensure((size_t)nq * S * 4));
+  HR_CUDA(cudaMemsetAsync(h->tau.p, 0, (size_t)nq * 8, st));
+  bm25_plan_terms_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(
+      h->indptr, h->idf, h->V, qi_dev, qt_dev, (int)nq, h->plan_nt.as<int>(), h->plan_start.as<int64_t>(),
+      h->plan_len.as<uint32_t>(), h->plan_wgt.as<float>(), touched_dev);
+  HR_LAUNCHED();
+  {
+    dim3 grid((unsigned)nq, (unsigned)((nwin + 1 + 255) / 256));
+    bm25_plan_cursors_kernel<<<grid, 256, 0, st>>>(h->post_doc, qi_dev, h->plan_nt.as<int>(),
+                                                   h->plan_start.as<int64_t>(), h->plan_len.as<uint32_t>(), nwin,
+                                                   h->plan_cur.as<uint32_t>());
     HR_LAUNCHED();
   }
+  HR_CUDA(cudaFuncSetAttribute(bm25_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  {
+    dim3 grid((unsigned)nq, (unsigned)S);
+    bm25_window_kernel<<<grid, kBwThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
+                                                       h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
+                                                       h->plan_cur.as<uint32_t>(), nwin, wpc, (int)S, k, kcp,
+                                                       h->keys.as<uint64_t>(), h->ns.as<int>(),
+                                                       h->tau.as<unsigned long long>());
+    HR_LAUNCHED();
+  }
+  bm25_merge_kernel<<<(unsigned)nq, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), (int)S, k, k, h->id_base,
+                                                  S_dev, I_dev);
+  HR_LAUNCHED();
   return HR_OK;
 }
 
-extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t* q_terms, int64_t nq, int k,
-                              float* S, int64_t* I, int io_on_device, void* stream, int64_t* postings_touched) {
+extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t* q_terms, int64_t nq,
+                              int64_t n_terms, int k, float* S, int64_t* I, int io_on_device, void* stream,
+                              int64_t* postings_touched) {
   if (!h) return set_err(HR_ERR_INVALID, "null bm25");
   if (nq < 0) return set_err(HR_ERR_INVALID, "nq < 0");
   if (k <= 0 || k > kBmMaxK) return set_err(HR_ERR_INVALID, "bm25 k must be in [1, 128]");
@@ -916,9 +949,10 @@ extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t
   HR_TRY(h->touched.ensure(8));
   HR_CUDA(cudaMemsetAsync(h->touched.p, 0, 8, st));
   if (io_on_device) {
-    HR_TRY(bm25_search_dev(h, q_indptr, q_terms, nq, k, S, I, st, h->touched.as<unsigned long long>()));
+    HR_TRY(bm25_search_dev(h, q_indptr, q_terms, nq, n_terms, k, S, I, st, h->touched.as<unsigned long long>()));
   } else {
     const int64_t nterms = q_indptr[nq];
+    if (n_terms >= 0 && n_terms < nterms) return set_err(HR_ERR_INVALID, "n_terms is smaller than q_indptr[nq]");
     for (int64_t i = 0; i < nq; ++i) {
       if (q_indptr[i + 1] < q_indptr[i]) return set_err(HR_ERR_INVALID, "q_indptr must be non-decreasing");
       if (q_indptr[i + 1] - q_indptr[i] > kBmMaxTerms)
@@ -930,7 +964,7 @@ extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t
     HR_TRY(h->io_I.ensure((size_t)nq * k * 8));
     HR_CUDA(cudaMemcpyAsync(h->io_qi.p, q_indptr, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, st));
     if (nterms > 0) HR_CUDA(cudaMemcpyAsync(h->io_qt.p, q_terms, (size_t)nterms * 4, cudaMemcpyHostToDevice, st));
-    HR_TRY(bm25_search_dev(h, h->io_qi.as<int32_t>(), h->io_qt.as<int32_t>(), nq, k, h->io_S.as<float>(),
+    HR_TRY(bm25_search_dev(h, h->io_qi.as<int32_t>(), h->io_qt.as<int32_t>(), nq, nterms, k, h->io_S.as<float>(),
                            h->io_I.as<int64_t>(), st, h->touched.as<unsigned long long>()));
     HR_CUDA(cudaMemcpyAsync(S, h->io_S.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     HR_CUDA(cudaMemcpyAsync(I, h->io_I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
@@ -977,7 +1011,7 @@ extern "C" int hr_fuse(const float* dense_D, const int64_t* dense_I, const float
 // -------------------------------------------------------------------------------------------------
 
 extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
-                           const int32_t* q_terms, int64_t nq, int top_k, int kc, int mode, float w_vec,
+                           const int32_t* q_terms, int64_t nq, int64_t n_terms, int top_k, int kc, int mode, float w_vec,
                            float w_bm25, float* out_S, int64_t* out_I, int io_on_device, void* stream) {
   if (!ix) return set_err(HR_ERR_INVALID, "null index");
   if (nq < 0 || top_k <= 0) return set_err(HR_ERR_INVALID, "bad retrieve arguments");
@@ -1006,6 +1040,7 @@ extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int3
     qd = rs.q.as<float>();
     if (bm) {
       const int64_t nterms = q_indptr[nq];
+      n_terms = nterms;
       for (int64_t i = 0; i < nq; ++i)
         if (q_indptr[i + 1] < q_indptr[i] || q_indptr[i + 1] - q_indptr[i] > kBmMaxTerms)
           return set_err(HR_ERR_INVALID, "bad q_indptr (non-monotone, or a query has more than 64 terms)");
@@ -1023,7 +1058,7 @@ extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int3
   }
   // BM25 first (asynchronous), then the dense search (which synchronises), then fusion
   if (bm) {
-    HR_TRY(bm25_search_dev(bm, qid, qtd, nq, kc, rs.bS.as<float>(), rs.bI.as<int64_t>(), st, nullptr));
+    HR_TRY(bm25_search_dev(bm, qid, qtd, nq, n_terms, kc, rs.bS.as<float>(), rs.bI.as<int64_t>(), st, nullptr));
   } else {
     fill_pad_kernel<<<(int)std::min<int64_t>((nq * kc + 255) / 256, 1024), 256, 0, st>>>(
         rs.bS.as<float>(), rs.bI.as<int64_t>(), nq * kc, 0.f);

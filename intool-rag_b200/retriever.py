@@ -68,7 +68,8 @@ class HybridRetriever:
             S = torch.empty((nq, top_k), dtype=torch.float32, device=q.device)
             I = torch.empty((nq, top_k), dtype=torch.int64, device=q.device)
             _lib.check(L.hr_retrieve(self.index._h, bm_h, q.data_ptr(), qi.data_ptr() if use_bm else None,
-                                     qt.data_ptr() if use_bm else None, nq, top_k, kc, _MODES[self.fusion],
+                                     qt.data_ptr() if use_bm else None, nq, int(qt.numel()) if use_bm else 0,
+                                     top_k, kc, _MODES[self.fusion],
                                      self.vector_weight, self.bm25_weight, S.data_ptr(), I.data_ptr(), 1,
                                      _lib.current_stream_ptr(self.index.device)))
             return S, I
@@ -84,7 +85,7 @@ class HybridRetriever:
         S = np.empty((nq, top_k), dtype=np.float32)
         I = np.empty((nq, top_k), dtype=np.int64)
         _lib.check(L.hr_retrieve(self.index._h, bm_h, q.ctypes.data, qi.ctypes.data if use_bm else None,
-                                 qt.ctypes.data if use_bm else None, nq, top_k, kc, _MODES[self.fusion],
+                                 qt.ctypes.data if use_bm else None, nq, int(qt.size) if use_bm else 0, top_k, kc, _MODES[self.fusion],
                                  self.vector_weight, self.bm25_weight, S.ctypes.data, I.ctypes.data, 0,
                                  _lib.current_stream_ptr(self.index.device)))
         return S, I
