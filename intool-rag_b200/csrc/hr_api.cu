@@ -831,8 +831,8 @@ extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, co
   const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
   const size_t nd = (size_t)std::max<int64_t>(n_docs, 1);
   if (cudaMalloc((void**)&h->indptr, (size_t)(vocab + 1) * 8) != cudaSuccess ||
-      cudaMalloc((void**)&h->post_doc, nz * 4) != cudaSuccess ||
-      cudaMalloc((void**)&h->post_imp, nz * 4) != cudaSuccess || cudaMalloc((void**)&h->idf, (size_t)vocab * 4) != cudaSuccess)
+      cudaMalloc((void**)&h->post_doc, (nz + 4) * 4) != cudaSuccess ||   // +4: the window kernel reads 16-byte groups
+      cudaMalloc((void**)&h->post_imp, (nz + 4) * 4) != cudaSuccess || cudaMalloc((void**)&h->idf, (size_t)vocab * 4) != cudaSuccess)
     return fail(HR_ERR_NOMEM, "cudaMalloc failed for the BM25 index");
   double avgdl = avgdl_global;
   if (cudaMemcpyAsync(h->indptr, h_indptr.data(), (size_t)(vocab + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
