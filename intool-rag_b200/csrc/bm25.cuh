@@ -36,8 +36,9 @@ constexpr int kBmMaxTerms = 64;   // raw terms per query
 constexpr int kBmMaxK = 128;      // candidate depth the kernel supports
 constexpr int kBwThreads = 256;
 constexpr int kBwWarps = kBwThreads / 32;
-constexpr int kBwWin = 15360;     // docs per window (60 KB of accumulators: three CTAs per SM)
-constexpr int kBwSlice = kBwWin / kBwWarps;
+constexpr int kBwCons = kBwWarps - 1;   // consumer warps; the last warp plans the next window
+constexpr int kBwSlice = 17 * 128;       // docs per consumer warp in the clear / sweep phases
+constexpr int kBwWin = kBwCons * kBwSlice;   // 15232 docs per window (59.5 KB of accumulators: three CTAs per SM)
 // dynamic shared memory: accumulators | warp key buffers (2*kcp keys each)
 __host__ __device__ constexpr int bw_smem_bytes(int kcp) { return kBwWin * 4 + kBwWarps * 2 * kcp * 8; }
 
@@ -167,8 +168,8 @@ constexpr int kBwHotCap = 1024;   // docs that may reach the threshold in one wi
 
 // One slot = kBwSlotLen consecutive postings of one term, starting at a 4-aligned global posting index;
 // [f, e) of them lie inside the current window's range of that term.  Slot g of a round is applied by
-// warp g % 8.  Slots are ordered by term; `need` counts the term boundaries before the slot inside its
-// round: a warp passes that many block barriers before it applies the slot, so postings of different
+// consumer warp g % 7.  Slots are ordered by term; `need` counts the term boundaries before the slot inside its
+// round: a warp passes that many consumer barriers before it applies the slot, so postings of different
 // terms never race on a document (inside one term doc ids are unique).
 struct __align__(16) BwSlot {
   uint32_t p_lo, p_hi;   // global posting index of the slot's first posting (multiple of 4)
@@ -176,22 +177,33 @@ struct __align__(16) BwSlot {
   float w;               // term weight (multiplicity * idf)
 };
 
-// Warp 0: describe slots [r0, r0 + kBwSlotCap) of the window whose cursors are in s_lo/s_hi (r0 < number of
-// slots, or the window is empty).  Lane l owns terms l and l + 32; slot numbers come from warp prefix sums.
-// s_meta[0] = slots in the window, s_meta[1] = barriers the round needs in total.
-__device__ __forceinline__ void bw_build_slots(int lane, int nt, const int64_t* s_start, const float* s_w,
-                                               const uint32_t* s_lo, const uint32_t* s_hi, int r0, BwSlot* slots,
-                                               int* s_meta) {
-  int64_t a[2] = {0, 0};
-  uint32_t n[2] = {0, 0};
-  int cnt[2] = {0, 0};
+// Per-term state of a query, kept in the registers of warp 0: lane l owns terms l and l + 32.
+struct BwTerms {
+  int64_t start[2];        // first posting of the list
+  float wgt[2];
+  uint32_t b0[2], b1[2], b2[2];   // cursors at the boundaries of window k, k+1, k+2 (k = current window)
+};
+
+// Warp 0: describe slots [r0, r0 + kBwSlotCap) of the window with cursors [lo, hi) per term (r0 < number of
+// slots, or the window is empty).  Slot numbers come from warp prefix sums.  meta[0] = slots in the window,
+// meta[1] = barriers the round needs in total.  With prefetch != 0 the posting ranges are also requested
+// into L2 (one bulk prefetch per array and term).
+__device__ __forceinline__ void bw_build_slots(int lane, const BwTerms& T, const uint32_t (&lo)[2], const uint32_t (&hi)[2],
+                                               int r0, BwSlot* slots, int* meta, const int32_t* post_doc,
+                                               const float* post_imp, bool prefetch) {
+  int64_t a[2];
+  uint32_t n[2];
+  int cnt[2];
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    const int term = lane + 32 * half;
-    if (term < nt) {
-      n[half] = s_hi[term] - s_lo[term];
-      a[half] = s_start[term] + s_lo[term];
-      if (n[half]) cnt[half] = (int)((a[half] + n[half] - (a[half] & ~(int64_t)3) + kBwSlotLen - 1) / kBwSlotLen);
+    n[half] = hi[half] - lo[half];
+    a[half] = T.start[half] + lo[half];
+    cnt[half] = n[half] ? (int)((a[half] + n[half] - (a[half] & ~(int64_t)3) + kBwSlotLen - 1) / kBwSlotLen) : 0;
+    if (prefetch && n[half]) {
+      const int64_t s0 = a[half] & ~(int64_t)3;
+      const uint32_t bytes = (uint32_t)(((a[half] + n[half] - s0 + 3) & ~(int64_t)3) * 4);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(post_doc + s0), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(post_imp + s0), "r"(bytes) : "memory");
     }
   }
   int iA = cnt[0], iB = cnt[1];
@@ -217,35 +229,50 @@ __device__ __forceinline__ void bw_build_slots(int lane, int nt, const int64_t* 
   else if (inB) rank0 = __shfl_sync(0xffffffffu, rank[1], __ffs(inB) - 1);
   const int last = min(nslots, r0 + kBwSlotCap) - 1;
   if (lane == 0) {
-    s_meta[0] = nslots;
-    if (nslots == 0) s_meta[1] = 0;
+    meta[0] = nslots;
+    if (nslots == 0) meta[1] = 0;
   }
+  // slot-parallel: lane takes slots r0 + lane, r0 + lane + 32, ...; the owning term is found by a binary
+  // search over the lanes' inclusive slot prefix sums (shuffles), then its data is fetched from that lane
+  const int incl[2] = {iA, totA + iB};
+  for (int g0 = r0; g0 <= last; g0 += 32) {
+    const int gg = g0 + lane;
+    const int half = gg >= totA ? 1 : 0;
+    int lo_l = 0, hi_l = 31;   // smallest lane whose inclusive prefix exceeds gg
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    if (cnt[half] > 0) {
-      const int term = lane + 32 * half;
-      const int64_t s0 = a[half] & ~(int64_t)3;
-      const int64_t end = a[half] + n[half];
-      const float wt = s_w[term];
-      const uint32_t need = (uint32_t)max(rank[half] - rank0, 0);
-      const int sl0 = max(0, r0 - off[half]), sl1 = min(cnt[half], r0 + kBwSlotCap - off[half]);
-      for (int sl = sl0; sl < sl1; ++sl) {
-        const int64_t ps = s0 + (int64_t)sl * kBwSlotLen;
-        const uint32_t f = sl == 0 ? (uint32_t)(a[half] - s0) : 0u;
-        const uint32_t e = (uint32_t)min((int64_t)kBwSlotLen, end - ps);
-        BwSlot d;
-        d.p_lo = (uint32_t)ps;
-        d.p_hi = (uint32_t)(ps >> 32);
-        d.meta = f | (e << 8) | (need << 16);
-        d.w = wt;
-        slots[off[half] + sl - r0] = d;
-        if (off[half] + sl == last) s_meta[1] = (int)need;
-      }
+    for (int it = 0; it < 5; ++it) {
+      const int mid = (lo_l + hi_l) >> 1;
+      const int v0 = __shfl_sync(0xffffffffu, incl[0], mid), v1 = __shfl_sync(0xffffffffu, incl[1], mid);
+      if ((half ? v1 : v0) > gg) hi_l = mid; else lo_l = mid + 1;
+    }
+    const int src = lo_l;
+    const int64_t a0 = __shfl_sync(0xffffffffu, a[0], src), a1 = __shfl_sync(0xffffffffu, a[1], src);
+    const uint32_t n0 = __shfl_sync(0xffffffffu, n[0], src), n1 = __shfl_sync(0xffffffffu, n[1], src);
+    const int o0 = __shfl_sync(0xffffffffu, off[0], src), o1 = __shfl_sync(0xffffffffu, off[1], src);
+    const int r_0 = __shfl_sync(0xffffffffu, rank[0], src), r_1 = __shfl_sync(0xffffffffu, rank[1], src);
+    const float w0 = __shfl_sync(0xffffffffu, T.wgt[0], src), w1 = __shfl_sync(0xffffffffu, T.wgt[1], src);
+    if (gg <= last) {
+      const int64_t at = half ? a1 : a0;
+      const int64_t s0 = at & ~(int64_t)3;
+      const int64_t end = at + (half ? n1 : n0);
+      const int sl = gg - (half ? o1 : o0);
+      const int64_t ps = s0 + (int64_t)sl * kBwSlotLen;
+      const uint32_t need = (uint32_t)max((half ? r_1 : r_0) - rank0, 0);
+      const uint32_t f = sl == 0 ? (uint32_t)(at - s0) : 0u;
+      const uint32_t e = (uint32_t)min((int64_t)kBwSlotLen, end - ps);
+      BwSlot d;
+      d.p_lo = (uint32_t)ps;
+      d.p_hi = (uint32_t)(ps >> 32);
+      d.meta = f | (e << 8) | (need << 16);
+      d.w = half ? w1 : w0;
+      slots[gg - r0] = d;
+      if (gg == last) meta[1] = (int)need;
     }
   }
 }
 
-__device__ __forceinline__ void bw_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+// barrier 1: the consumer warps only (the planner warp never takes part in a term boundary)
+__device__ __forceinline__ void bw_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kBwCons * 32) : "memory"); }
 
 // Warp-collective append of a candidate key to the warp's key buffer (compaction by bitonic sort keeps the
 // best kc and raises the warp / CTA / query thresholds).
@@ -285,18 +312,15 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
                    const int32_t* __restrict__ q_indptr, const int* __restrict__ plan_nt,
                    const int64_t* __restrict__ plan_start, const float* __restrict__ plan_wgt,
                    const uint32_t* __restrict__ plan_cur, int64_t nwin, int wpc, int S, int kc, int kcp,
-                   uint64_t* __restrict__ out_keys, int* __restrict__ out_n, unsigned long long* __restrict__ tau_g) {
+                   uint64_t* __restrict__ out_keys, int* __restrict__ out_n, unsigned long long* __restrict__ tau_g, int flags) {
   extern __shared__ __align__(16) uint8_t bsm[];
   float* acc = (float*)bsm;
   uint64_t* cb_all = (uint64_t*)(bsm + kBwWin * 4);
-  __shared__ BwSlot s_slots[kBwSlotCap];
-  __shared__ int64_t s_start[kBmMaxTerms];
-  __shared__ float s_w[kBmMaxTerms];
-  __shared__ uint32_t s_lo[kBmMaxTerms], s_hi[kBmMaxTerms];
+  __shared__ BwSlot s_slots[2][kBwSlotCap];   // double buffered: warp 0 describes window k+1 during window k
+  __shared__ int s_meta[2][2];
   __shared__ uint16_t s_hot[kBwHotCap];
   __shared__ unsigned long long s_tau;
   __shared__ unsigned int s_nhot[2];
-  __shared__ int s_meta[2];
   __shared__ int s_wn[kBwWarps];
 
   const int q = blockIdx.x;
@@ -316,11 +340,21 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
   const int qa = q_indptr[q];
   const uint32_t* curq = plan_cur + (size_t)qa * (size_t)(nwin + 1);
   unsigned long long* tau_gq = tau_g + q;
-  if (tid < nt) {
-    s_start[tid] = plan_start[qa + tid];
-    s_w[tid] = plan_wgt[qa + tid];
-    s_lo[tid] = curq[(size_t)win0 * nt + tid];
-    s_hi[tid] = curq[(size_t)(win0 + 1) * nt + tid];
+  BwTerms T;
+  uint32_t nxt[2] = {0, 0};   // cursors at boundary k+3, in flight during window k
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int term = lane + 32 * half;
+    T.start[half] = 0;
+    T.wgt[half] = 0.f;
+    T.b0[half] = T.b1[half] = T.b2[half] = 0;
+    if (w == kBwCons && term < nt) {
+      T.start[half] = plan_start[qa + term];
+      T.wgt[half] = plan_wgt[qa + term];
+      T.b0[half] = curq[(size_t)win0 * nt + term];
+      T.b1[half] = curq[(size_t)(win0 + 1) * nt + term];
+      T.b2[half] = win0 + 2 <= nwin ? curq[(size_t)(win0 + 2) * nt + term] : T.b1[half];
+    }
   }
   if (tid == 0) {
     s_tau = *((volatile unsigned long long*)tau_gq);
@@ -328,63 +362,75 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
     s_nhot[1] = 0;
   }
   for (int i = tid * 4; i < kBwWin; i += kBwThreads * 4) *reinterpret_cast<float4*>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  if (w == 0) bw_build_slots(lane, nt, s_start, s_w, s_lo, s_hi, 0, s_slots, s_meta);
+  const bool planner = w == kBwCons;
+  if (planner) bw_build_slots(lane, T, T.b0, T.b1, 0, s_slots[win0 & 1], s_meta[win0 & 1], post_doc, post_imp, false);
   __syncthreads();
 
   int cbn = 0;                 // keys in this warp's buffer (warp-uniform)
   unsigned long long tau = 0;  // this warp's threshold key: a lower bound of the query's kc-th best
   float tau_f = 0.f;
-  float* slice = acc + w * kBwSlice;
+  float* slice = acc + (planner ? 0 : w) * kBwSlice;
+  // one batch of slots per warp in registers
+  int4 dd[kBwBatch];
+  float4 vv[kBwBatch];
+  uint32_t meta[kBwBatch];
+  float ww[kBwBatch];
+  auto load_batch = [&](const BwSlot* tab, int nr, int b0) {
+#pragma unroll
+    for (int j = 0; j < kBwBatch; ++j) {
+      const int gr = b0 + w + kBwCons * j;
+      meta[j] = 0;
+      ww[j] = 0.f;
+      dd[j] = make_int4(0, 0, 0, 0);
+      vv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < nr) {
+        const BwSlot e = tab[gr];
+        meta[j] = e.meta;
+        ww[j] = e.w;
+        if ((uint32_t)(4 * lane) < ((e.meta >> 8) & 0xFFu)) {
+          const int64_t p = (int64_t)(((uint64_t)e.p_hi << 32) | e.p_lo) + 4 * lane;
+          dd[j] = __ldg(reinterpret_cast<const int4*>(post_doc + p));
+          vv[j] = __ldg(reinterpret_cast<const float4*>(post_imp + p));
+        }
+      }
+    }
+  };
+  if (!planner) load_batch(s_slots[win0 & 1], min(kBwSlotCap, s_meta[win0 & 1][0]), 0);
   for (int64_t win = win0; win < win1; ++win) {
     const int32_t docbase = (int32_t)(win * kBwWin);
-    unsigned int* nhot_p = &s_nhot[win & 1];
-    // cursors of the next window (consumed at the end of this one)
-    uint32_t nxtA = 0, nxtB = 0;   // warp 0: lane l keeps terms l and l + 32
-    if (w == 0 && win + 2 <= nwin) {
-      if (lane < nt) nxtA = __ldg(curq + (size_t)(win + 2) * nt + lane);
-      if (lane + 32 < nt) nxtB = __ldg(curq + (size_t)(win + 2) * nt + lane + 32);
-    }
+    const int buf = (int)(win & 1);
+    unsigned int* nhot_p = &s_nhot[buf];
     unsigned long long gt = 0;
-    if (tid == 0) gt = *((volatile unsigned long long*)tau_gq);
+    if (planner) {
+      if (lane == 0) gt = *((volatile unsigned long long*)tau_gq);
+      // cursors three boundaries ahead; slots of the next window (its postings go to L2 meanwhile)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int term = lane + 32 * half;
+        nxt[half] = T.b2[half];
+        if (term < nt && win + 3 <= nwin) nxt[half] = __ldg(curq + (size_t)(win + 3) * nt + term);
+      }
+      if (win + 1 < win1)
+        bw_build_slots(lane, T, T.b1, T.b2, 0, s_slots[buf ^ 1], s_meta[buf ^ 1], post_doc, post_imp, !(flags & 1));
+    }
     // ---- apply: slot g of a round belongs to warp g % 8; kBwBatch slots in flight per warp ----
     const float tau_pos = tau_f > 0.f ? tau_f : 1.4e-45f;   // x >= tau_pos <=> x > 0 && x >= tau_f
-    const int nslots = s_meta[0];
+    const int nslots = s_meta[buf][0];
     for (int r0 = 0; r0 < nslots; r0 += kBwSlotCap) {
       if (r0 > 0) {   // more slots than the staging table holds: describe the next round
         __syncthreads();
-        if (w == 0) bw_build_slots(lane, nt, s_start, s_w, s_lo, s_hi, r0, s_slots, s_meta);
+        if (planner) bw_build_slots(lane, T, T.b0, T.b1, r0, s_slots[buf], s_meta[buf], post_doc, post_imp, false);
         __syncthreads();
       }
       const int nr = min(kBwSlotCap, nslots - r0);
-      const int total_need = s_meta[1];
+      const int total_need = s_meta[buf][1];
+      if (planner) continue;
       int done = 0;   // barriers this warp has passed in this round
-      for (int b0 = 0; b0 < nr; b0 += kBwWarps * kBwBatch) {
-        int4 dd[kBwBatch];
-        float4 vv[kBwBatch];
-        uint32_t meta[kBwBatch];
-        float ww[kBwBatch];
+      for (int b0 = 0; b0 < nr; b0 += kBwCons * kBwBatch) {
+        if (r0 + b0 > 0 || ((flags & 2) && win > win0)) load_batch(s_slots[buf], nr, b0);   // the window's first batch is already in flight
 #pragma unroll
         for (int j = 0; j < kBwBatch; ++j) {
-          const int gr = b0 + w + kBwWarps * j;
-          meta[j] = 0;
-          ww[j] = 0.f;
-          dd[j] = make_int4(0, 0, 0, 0);
-          vv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gr < nr) {
-            const BwSlot e = s_slots[gr];
-            meta[j] = e.meta;
-            ww[j] = e.w;
-            if ((uint32_t)(4 * lane) < ((e.meta >> 8) & 0xFFu)) {
-              const int64_t p = (int64_t)(((uint64_t)e.p_hi << 32) | e.p_lo) + 4 * lane;
-              dd[j] = __ldg(reinterpret_cast<const int4*>(post_doc + p));
-              vv[j] = __ldg(reinterpret_cast<const float4*>(post_imp + p));
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < kBwBatch; ++j) {
-          const int gr = b0 + w + kBwWarps * j;
+          const int gr = b0 + w + kBwCons * j;
           if (gr < nr) {   // warp-uniform
             const int need = (int)(meta[j] >> 16);
             while (done < need) {
@@ -396,17 +442,20 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
             const float iv[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
             float xs[4];
             int offs[4];
+            bool valid[4];
             bool hot = false;
+            // the four docs of a lane are distinct (one posting list): read all, then add, then write
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4) {
               const uint32_t idx = 4u * lane + e4;
-              const bool valid = idx >= f && idx < e;
-              offs[e4] = valid ? dv[e4] - docbase : 0;
-              xs[e4] = 0.f;
-              if (valid) {
-                xs[e4] = fmaf(ww[j], iv[e4], acc[offs[e4]]);
-                acc[offs[e4]] = xs[e4];
-              }
+              valid[e4] = idx >= f && idx < e;
+              offs[e4] = valid[e4] ? dv[e4] - docbase : 0;
+              xs[e4] = acc[offs[e4]];
+            }
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              xs[e4] = valid[e4] ? fmaf(ww[j], iv[e4], xs[e4]) : 0.f;
+              if (valid[e4]) acc[offs[e4]] = xs[e4];
               hot = hot || xs[e4] >= tau_pos;
             }
             // docs whose running score reached the threshold go to the hot list (the thread applying a doc's
@@ -437,8 +486,10 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
       }
     }
     // ---- end of window ----
-    if (tid == 0 && gt > s_tau) s_tau = gt;   // elsewhere s_tau only changes by atomicMax after the next barrier
+    if (planner && lane == 0 && gt > s_tau) s_tau = gt;   // elsewhere s_tau only changes by atomicMax after the next barrier
     __syncthreads();
+    // the next window's first batch of postings starts its trip now (its slots were described during this window)
+    if (!planner && win + 1 < win1 && !(flags & 2)) load_batch(s_slots[buf ^ 1], min(kBwSlotCap, s_meta[buf ^ 1][0]), 0);
     const unsigned nhot = *((volatile unsigned int*)nhot_p);
     {
       const unsigned long long ct = *((volatile unsigned long long*)&s_tau);
@@ -451,7 +502,7 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
       // cold thresholds: sweep the warp's slice, extract and clear
       const int32_t s0 = docbase + w * kBwSlice;
 #pragma unroll 2
-      for (int j = lane * 4; j < kBwSlice; j += 128) {
+      for (int j = lane * 4; !planner && j < kBwSlice; j += 128) {
         float4 v = *reinterpret_cast<float4*>(slice + j);
         const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
         *reinterpret_cast<float4*>(slice + j) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -472,7 +523,7 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
     } else {
       if (nhot > 0) {
         // the listed docs only: the first reader of a doc takes its score (exchange with 0), duplicates see 0
-        for (unsigned i0 = 0; i0 < nhot; i0 += kBwThreads) {
+        for (unsigned i0 = 0; !planner && i0 < nhot; i0 += kBwCons * 32) {
           const unsigned i = i0 + tid;
           unsigned long long key = 0;
           bool take = false;
@@ -488,23 +539,21 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
         }
         __syncthreads();   // uniform (nhot is): the sweep below must not clear a listed doc before it is read
       }
+      if (!planner) {
 #pragma unroll
-      for (int j = lane * 4; j < kBwSlice; j += 128) *reinterpret_cast<float4*>(slice + j) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (w == 0 && win + 1 < win1) {   // next window: rotate the cursors, describe its slots, reset its hot counter
-      if (lane < nt) {
-        s_lo[lane] = s_hi[lane];
-        s_hi[lane] = nxtA;
+        for (int j = lane * 4; j < kBwSlice; j += 128) *reinterpret_cast<float4*>(slice + j) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (lane + 32 < nt) {
-        s_lo[lane + 32] = s_hi[lane + 32];
-        s_hi[lane + 32] = nxtB;
-      }
-      if (lane == 0) s_nhot[(win + 1) & 1] = 0;
-      __syncwarp();
-      bw_build_slots(lane, nt, s_start, s_w, s_lo, s_hi, 0, s_slots, s_meta);
     }
-    __syncthreads();   // clears, cursors and slots visible before the next window
+    if (planner) {   // advance the cursors by one window
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        T.b0[half] = T.b1[half];
+        T.b1[half] = T.b2[half];
+        T.b2[half] = nxt[half];
+      }
+      if (lane == 0) s_nhot[buf ^ 1] = 0;
+    }
+    __syncthreads();   // clears visible before the next window's first slot is applied
   }
   // ---- warp list -> sorted top-kc ----
   for (int i = cbn + lane; i < cbcap; i += 32) cb[i] = 0;

@@ -927,7 +927,8 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
                                                        h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
                                                        h->plan_cur.as<uint32_t>(), nwin, wpc, (int)S, k, kcp,
                                                        h->keys.as<uint64_t>(), h->ns.as<int>(),
-                                                       h->tau.as<unsigned long long>());
+                                                       h->tau.as<unsigned long long>(),
+                                                       getenv("HR_BM25_FLAGS") ? atoi(getenv("HR_BM25_FLAGS")) : 0);
     HR_LAUNCHED();
   }
   bm25_merge_kernel<<<(unsigned)nq, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), (int)S, k, k, h->id_base,
