@@ -37,6 +37,10 @@ extern "C" {
 
 #define HR_STORAGE_F32 0  /* fp32 rows, TF32 tensor-core filter + exact fp32 re-score      */
 #define HR_STORAGE_BF16 1 /* bf16 rows (fp32 accumulate), bf16 filter + exact re-score    */
+/* fp32 rows (results, reconstruct and save identical to HR_STORAGE_F32) plus a bf16 shadow copy
+ * that the tensor-core filter streams instead: half the scan bytes, twice the MMA rate,
+ * 1.5x the memory.  The exact fp32 re-score + certificate make the answers the same. */
+#define HR_STORAGE_F32_SHADOW16 2
 
 /* dense search strategy (hr_index_set_mode) */
 #define HR_MODE_AUTO 0      /* tcgen05 filter scan + exact re-score + certified fallback  */

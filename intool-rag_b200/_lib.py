@@ -12,6 +12,7 @@ METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 STORAGE_F32 = 0
 STORAGE_BF16 = 1
+STORAGE_F32_SHADOW16 = 2
 MODE_AUTO = 0
 MODE_EXACT_SIMT = 1
 FUSE_WEIGHTED = 0

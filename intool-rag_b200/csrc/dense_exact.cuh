@@ -91,6 +91,19 @@ __global__ void convert_pad_norm_kernel(const float* __restrict__ src, int64_t n
   }
 }
 
+// fp32 rows (already padded) -> bf16 shadow rows for the tensor-core filter (HR_STORAGE_F32_SHADOW16)
+__global__ void shadow_bf16_kernel(const float* __restrict__ src, int64_t n_elems, __nv_bfloat16* __restrict__ dst) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  for (; i < n_elems; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  }
+}
+
 // queries fp32 [nq, d] -> padded fp32 [nq, ld] (+ optional bf16 copy for the bf16 filter)
 // rows [nq, nq_rows) are written as zeros: the TMA box of a small batch then still reads >= 32 distinct
 // cache lines per K block instead of every SM hammering the same line of a 1-row query matrix.

@@ -144,7 +144,8 @@ struct hr_index {
   int elem = 4;
   int num_sms = 148;
   int64_t ntotal = 0, capacity = 0, id_base = 0;
-  void* x = nullptr;
+  void* x = nullptr;           // exact rows: fp32 (F32, F32_SHADOW16) or bf16 (BF16), [capacity][ld]
+  __nv_bfloat16* xs = nullptr;  // F32_SHADOW16 only: bf16 copy of the rows for the tensor-core filter, [capacity][ld]
   float* norms = nullptr;
   unsigned int* max_norm2 = nullptr;  // ordered-uint of max |x|^2
   DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_n, tprime, flagged, counters;
@@ -155,6 +156,10 @@ struct hr_index {
 };
 
 static size_t row_bytes(const hr_index* h) { return (size_t)h->ld * h->elem; }
+// the rows the tensor-core filter streams: the exact rows, or their bf16 shadow
+static bool filter_is_bf16(const hr_index* h) { return h->storage != HR_STORAGE_F32; }
+static const void* filter_rows(const hr_index* h) { return h->storage == HR_STORAGE_F32_SHADOW16 ? (const void*)h->xs : (const void*)h->x; }
+static int filter_elem(const hr_index* h) { return filter_is_bf16(h) ? 2 : 4; }
 
 extern "C" const char* hr_last_error(void) { return g_err.c_str(); }
 extern "C" int hr_version(void) { return 100; }
@@ -178,8 +183,8 @@ extern "C" int hr_index_create(int d, int metric, int storage_dtype, int device,
   if (d <= 0 || d > 65536) return set_err(HR_ERR_INVALID, "d must be in [1, 65536]");
   if (metric != HR_METRIC_INNER_PRODUCT && metric != HR_METRIC_L2)
     return set_err(HR_ERR_INVALID, "metric must be METRIC_INNER_PRODUCT (0) or METRIC_L2 (1)");
-  if (storage_dtype != HR_STORAGE_F32 && storage_dtype != HR_STORAGE_BF16)
-    return set_err(HR_ERR_INVALID, "storage dtype must be HR_STORAGE_F32 or HR_STORAGE_BF16");
+  if (storage_dtype != HR_STORAGE_F32 && storage_dtype != HR_STORAGE_BF16 && storage_dtype != HR_STORAGE_F32_SHADOW16)
+    return set_err(HR_ERR_INVALID, "storage dtype must be HR_STORAGE_F32, HR_STORAGE_BF16 or HR_STORAGE_F32_SHADOW16");
   int ndev = 0;
   HR_TRY(hr_device_count(&ndev));
   if (ndev <= 0) return set_err(HR_ERR_CUDA, "no CUDA device (hr_b200 has no CPU fallback)");
@@ -198,8 +203,9 @@ extern "C" int hr_index_create(int d, int metric, int storage_dtype, int device,
   h->metric = metric;
   h->storage = storage_dtype;
   h->device = device;
-  h->elem = storage_dtype == HR_STORAGE_F32 ? 4 : 2;
-  const int kelems = 128 / h->elem;  // elements per 128-byte K block
+  h->elem = storage_dtype == HR_STORAGE_BF16 ? 2 : 4;
+  // elements per 128-byte K block of the filter's rows (the shadow shares ld with the fp32 rows)
+  const int kelems = storage_dtype == HR_STORAGE_F32 ? 32 : 64;
   h->ld = ((d + kelems - 1) / kelems) * kelems;
   h->num_sms = prop.multiProcessorCount;
   if (cudaMalloc((void**)&h->max_norm2, sizeof(unsigned int)) != cudaSuccess ||
@@ -218,6 +224,7 @@ extern "C" int hr_index_destroy(hr_index* h) {
   if (!h) return HR_OK;
   DeviceGuard g(h->device);
   if (h->x) cudaFree(h->x);
+  if (h->xs) cudaFree(h->xs);
   if (h->norms) cudaFree(h->norms);
   if (h->max_norm2) cudaFree(h->max_norm2);
   if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -235,22 +242,29 @@ extern "C" int hr_index_destroy(hr_index* h) {
 static int index_grow(hr_index* h, int64_t need, cudaStream_t st) {
   if (need <= h->capacity) return HR_OK;
   void* nx = nullptr;
+  void* ns = nullptr;
   float* nn = nullptr;
+  const bool shadow = h->storage == HR_STORAGE_F32_SHADOW16;
   cudaError_t e = cudaMalloc(&nx, (size_t)need * row_bytes(h));
   if (e == cudaSuccess) e = cudaMalloc((void**)&nn, (size_t)need * sizeof(float));
+  if (e == cudaSuccess && shadow) e = cudaMalloc(&ns, (size_t)need * h->ld * 2);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     if (nx) cudaFree(nx);
+    if (nn) cudaFree(nn);
     return set_err(HR_ERR_NOMEM, "cudaMalloc failed while growing the index (corpus does not fit in HBM?)");
   }
   if (h->ntotal > 0) {
     HR_CUDA(cudaMemcpyAsync(nx, h->x, (size_t)h->ntotal * row_bytes(h), cudaMemcpyDeviceToDevice, st));
     HR_CUDA(cudaMemcpyAsync(nn, h->norms, (size_t)h->ntotal * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (shadow) HR_CUDA(cudaMemcpyAsync(ns, h->xs, (size_t)h->ntotal * h->ld * 2, cudaMemcpyDeviceToDevice, st));
     HR_CUDA(cudaStreamSynchronize(st));
   }
   if (h->x) cudaFree(h->x);
+  if (h->xs) cudaFree(h->xs);
   if (h->norms) cudaFree(h->norms);
   h->x = nx;
+  h->xs = (__nv_bfloat16*)ns;
   h->norms = nn;
   h->capacity = need;
   return HR_OK;
@@ -287,10 +301,16 @@ extern "C" int hr_index_add(hr_index* h, const float* x, int64_t n, int is_devic
     }
     const int64_t row0 = h->ntotal + r0;
     const int blocks = (int)std::min<int64_t>((nr + 7) / 8, (int64_t)h->num_sms * 8);
-    if (h->storage == HR_STORAGE_F32)
+    if (h->storage != HR_STORAGE_BF16) {
       convert_pad_norm_kernel<float><<<blocks, 256, 0, st>>>(src, nr, h->d, (float*)h->x + row0 * h->ld, h->ld,
                                                             h->norms + row0, h->max_norm2);
-    else
+      if (h->storage == HR_STORAGE_F32_SHADOW16) {
+        HR_LAUNCHED();
+        const int64_t tot = nr * (int64_t)h->ld;
+        shadow_bf16_kernel<<<(int)std::min<int64_t>((tot / 4 + 255) / 256, (int64_t)h->num_sms * 16), 256, 0, st>>>(
+            (const float*)h->x + row0 * h->ld, tot, h->xs + row0 * h->ld);
+      }
+    } else
       convert_pad_norm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
           src, nr, h->d, (__nv_bfloat16*)h->x + row0 * h->ld, h->ld, h->norms + row0, h->max_norm2);
     HR_LAUNCHED();
@@ -355,7 +375,7 @@ extern "C" int hr_index_reconstruct(hr_index* h, int64_t i0, int64_t n, float* o
     const int64_t nr = std::min(chunk, n - r0);
     HR_TRY(h->stage.ensure((size_t)nr * h->d * 4));
     const int blocks = (int)std::min<int64_t>((nr * h->d + 255) / 256, 4096);
-    if (h->storage == HR_STORAGE_F32)
+    if (h->elem == 4)
       reconstruct_kernel<float><<<blocks, 256>>>((const float*)h->x, h->ld, h->d, i0 + r0, nr, h->stage.as<float>());
     else
       reconstruct_kernel<__nv_bfloat16><<<blocks, 256>>>((const __nv_bfloat16*)h->x, h->ld, h->d, i0 + r0, nr,
@@ -482,7 +502,8 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     return HR_OK;
   }
   const bool use_tc = (h->mode == HR_MODE_AUTO) && k <= 128;
-  const int KL = list_len_for_k(k);
+  // the bf16 shadow doubles the filter's error bound: a deeper shortlist keeps the certificate's margin
+  const int KL = h->storage == HR_STORAGE_F32_SHADOW16 ? std::min(256, 2 * list_len_for_k(k)) : list_len_for_k(k);
   const int num_ctiles = (int)((h->ntotal + kScanBN - 1) / kScanBN);
   const int grid = std::min(num_ctiles, h->num_sms);
   h->stats.mode_used = use_tc ? HR_MODE_AUTO : HR_MODE_EXACT_SIMT;
@@ -496,19 +517,19 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     int64_t* Ib = I_dev + q0 * k;
     const int nbp = std::max(nb, 32);  // query rows materialised for the TMA (zero rows beyond nb)
     HR_TRY(h->qpad.ensure((size_t)nbp * h->ld * 4));
-    if (h->storage == HR_STORAGE_BF16) HR_TRY(h->qh.ensure((size_t)nbp * h->ld * 2));
+    if (filter_is_bf16(h)) HR_TRY(h->qh.ensure((size_t)nbp * h->ld * 2));
     {
       const int64_t tot = (int64_t)nbp * h->ld;
       pad_queries_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 2048), 256, 0, st>>>(
           q_dev + q0 * h->d, nb, nbp, h->d, h->ld, h->qpad.as<float>(),
-          h->storage == HR_STORAGE_BF16 ? h->qh.as<__nv_bfloat16>() : nullptr);
+          filter_is_bf16(h) ? h->qh.as<__nv_bfloat16>() : nullptr);
       HR_LAUNCHED();
     }
     HR_TRY(h->ex_sel.ensure((size_t)nb * 4));
     if (!use_tc) {
       iota_kernel<<<(nb + 255) / 256, 256, 0, st>>>(h->ex_sel.as<int>(), nb, 0);
       HR_LAUNCHED();
-      if (h->storage == HR_STORAGE_F32) HR_TRY(launch_exact<float>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st));
+      if (h->elem == 4) HR_TRY(launch_exact<float>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st));
       else HR_TRY(launch_exact<__nv_bfloat16>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st));
       continue;
     }
@@ -524,13 +545,13 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     HR_CUDA(cudaMemsetAsync(h->tau_g.p, 0, (size_t)nb * 4, st));
     HR_CUDA(cudaMemsetAsync(h->counters.p, 0, 16, st));
     CUtensorMap tq, tx;
-    const void* qsrc = h->storage == HR_STORAGE_F32 ? (const void*)h->qpad.p : (const void*)h->qh.p;
-    HR_TRY(make_tmap(&tq, qsrc, nbp, h->ld, h->elem, kScanBM));
-    HR_TRY(make_tmap(&tx, h->x, h->ntotal, h->ld, h->elem, kScanBN));
+    const void* qsrc = filter_is_bf16(h) ? (const void*)h->qh.p : (const void*)h->qpad.p;
+    HR_TRY(make_tmap(&tq, qsrc, nbp, h->ld, filter_elem(h), kScanBM));
+    HR_TRY(make_tmap(&tx, filter_rows(h), h->ntotal, h->ld, filter_elem(h), kScanBN));
     ScanParams p;
     p.N = h->ntotal;
     p.nq = nb;
-    p.kblocks = (int)(row_bytes(h) / 128);
+    p.kblocks = (int)((size_t)h->ld * filter_elem(h) / 128);
     p.KL = KL;
     p.num_qtiles = (nb + kScanBM - 1) / kScanBM;
     p.norms = h->norms;
@@ -540,18 +561,18 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     // batches of more than 128 queries run on CTA pairs (cta_group::2, 128-row corpus halves per CTA)
     const bool use_pair = nb > kScanBM && h->num_sms >= 2 && !getenv("HR_NO_PAIR");
     CUtensorMap tx2;
-    if (use_pair) HR_TRY(make_tmap(&tx2, h->x, h->ntotal, h->ld, h->elem, 128));
+    if (use_pair) HR_TRY(make_tmap(&tx2, filter_rows(h), h->ntotal, h->ld, filter_elem(h), 128));
     auto run_scan = [&](int g) -> int {
       if (use_pair) {
         const int g2 = std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1);
-        if (h->storage == HR_STORAGE_F32) {
+        if (!filter_is_bf16(h)) {
           if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan2<0, 0>(h, tq, tx2, p, g2, st);
           return launch_scan2<0, 1>(h, tq, tx2, p, g2, st);
         }
         if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan2<1, 0>(h, tq, tx2, p, g2, st);
         return launch_scan2<1, 1>(h, tq, tx2, p, g2, st);
       }
-      if (h->storage == HR_STORAGE_F32) {
+      if (!filter_is_bf16(h)) {
         if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<0, 0>(h, tq, tx, p, g, st);
         return launch_scan<0, 1>(h, tq, tx, p, g, st);
       }
@@ -591,8 +612,9 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     HR_LAUNCHED();
     // worst-case relative error of the filter score: both operands lose <= 2^-10 (tf32 truncation) or the
     // query loses <= 2^-9 (bf16 rounding; bf16 rows are exact), plus fp32 accumulation over d terms
-    const float c_rel = 1.96e-3f + 2.4e-7f * (float)h->ld;
-    if (h->storage == HR_STORAGE_F32) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_rel, Db, Ib, st));
+    // (shadow: the stored row is rounded to bf16 as well, 2^-9 on each operand)
+    const float c_rel = (h->storage == HR_STORAGE_F32_SHADOW16 ? 3.92e-3f : 1.96e-3f) + 2.4e-7f * (float)h->ld;
+    if (h->elem == 4) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_rel, Db, Ib, st));
     else HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_rel, Db, Ib, st));
     HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 8, cudaMemcpyDeviceToHost, st));
     HR_CUDA(cudaStreamSynchronize(st));
@@ -602,7 +624,7 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     h->stats.flagged += nflag;
     h->stats.overflow += h->h_counters[1];
     if (nflag > 0) {
-      if (h->storage == HR_STORAGE_F32) HR_TRY(launch_exact<float>(h, h->flagged.as<int>(), nflag, k, Db, Ib, st));
+      if (h->elem == 4) HR_TRY(launch_exact<float>(h, h->flagged.as<int>(), nflag, k, Db, Ib, st));
       else HR_TRY(launch_exact<__nv_bfloat16>(h, h->flagged.as<int>(), nflag, k, Db, Ib, st));
     }
   }

@@ -21,7 +21,9 @@ from .config import default_device
 METRIC_INNER_PRODUCT = _lib.METRIC_INNER_PRODUCT
 METRIC_L2 = _lib.METRIC_L2
 _STORAGE = {"f32": _lib.STORAGE_F32, "fp32": _lib.STORAGE_F32, "float32": _lib.STORAGE_F32,
-            "bf16": _lib.STORAGE_BF16, "bfloat16": _lib.STORAGE_BF16}
+            "bf16": _lib.STORAGE_BF16, "bfloat16": _lib.STORAGE_BF16,
+            "f32+bf16": _lib.STORAGE_F32_SHADOW16, "f32_shadow16": _lib.STORAGE_F32_SHADOW16}
+_STORAGE_NAME = {_lib.STORAGE_F32: "f32", _lib.STORAGE_BF16: "bf16", _lib.STORAGE_F32_SHADOW16: "f32+bf16"}
 
 
 def _is_torch_cuda(x) -> bool:
@@ -52,7 +54,7 @@ class Index:
 
     @property
     def storage(self) -> str:
-        return "bf16" if _lib.lib().hr_index_storage(self._h) == _lib.STORAGE_BF16 else "f32"
+        return _STORAGE_NAME[int(_lib.lib().hr_index_storage(self._h))]
 
     def __del__(self):
         try:

@@ -196,6 +196,34 @@ def test_bf16_storage_matches_oracle_on_rounded_corpus(gpu):
         assert_topk_matches(D, I, Dr, Ir, TOL_F32, metric == "ip", f"bf16/{metric}")
 
 
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_bf16_shadow_filter_gives_the_fp32_answers_bit_for_bit(gpu, metric):
+    """storage 'f32+bf16': the filter streams a bf16 copy of the rows, the re-score reads the fp32
+    rows, so D and I must equal the plain fp32 index exactly (and reconstruct / file bytes too)."""
+    n, d, nq = 60000, 200, 300           # d not a multiple of 64: both row layouts are padded
+    x = synth.dense_corpus_np(n, d)
+    x[500:520] = x[3]                     # a run of duplicates: certificate -> exact fallback
+    q = synth.dense_queries_np(x, nq)
+    q[0] = x[3]
+    a, b = _mk(metric, d), _mk(metric, d, storage="f32+bf16")
+    a.add(x[:25000]), a.add(x[25000:])
+    b.add(x[:25000]), b.add(x[25000:])
+    assert b.storage == "f32+bf16"
+    np.testing.assert_array_equal(b.reconstruct_n(24990, 20), x[24990:25010])
+    for k in (10, 50, 128):
+        Da, Ia = a.search(q, k)
+        Db, Ib = b.search(q, k)
+        assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db), (metric, k)
+        st = b.stats()
+        assert st["mode_used"] == 0 and st["list_len"] == min(256, 2 * a.stats()["list_len"])
+    assert b.stats()["flagged"] <= 3      # only the duplicate query (and near-ties) may need the exact scan
+    o = _oracle(metric, d)
+    o.add(x)
+    Dr, Ir = o.search(q, 10, precision="f64")
+    Db, Ib = b.search(q, 10)
+    assert_topk_matches(Db, Ib, Dr, Ir, TOL_F32, metric == "ip", f"shadow/{metric}")
+
+
 def test_l2_ip_equivalence_on_unit_norm(gpu):
     n, d = 30000, 96
     x = synth.dense_corpus_np(n, d)
