@@ -9,23 +9,26 @@
 // A search is three kernels:
 //   bm25_plan_terms_kernel   per query: de-duplicate the terms (first-occurrence order, multiplicity
 //                            folded into the weight), drop empty / out-of-vocabulary ones.
-//   bm25_plan_cursors_kernel per (query, term, window boundary): lower_bound of the boundary's first
-//                            doc id in the term's posting list.  The document axis is cut into
-//                            windows of kBwWin docs; with the cursor table every (query, window) is
-//                            an independent, exactly-known set of posting ranges.
-//   bm25_window_kernel       CTA = (query, span of consecutive windows).  The window's accumulators
-//                            (kBwWin fp32) live in shared memory.  The posting ranges of the window
-//                            are cut into slots of 128 postings (one warp, 16-byte loads, 4 postings
-//                            per lane); a warp loads kBwBatch slots at once (all loads in flight
-//                            before the first use), then applies them with plain shared-memory
-//                            read-modify-writes: doc ids inside one posting list are unique, and a
-//                            block barrier separates different terms (each slot carries the number of
-//                            barriers a warp must have passed before applying it), so no atomics are
-//                            needed and the fp32 summation order is fixed (term order): results are
-//                            deterministic.  A doc whose running score reaches the running threshold
-//                            is pushed to a small hot list; at the end of a window only the listed
-//                            docs are turned into candidates (warp-private key buffers, bitonic
-//                            compaction) and the accumulators are cleared with one vectorised sweep.
+//   bm25_plan_cursors_kernel per (query, term, slice boundary): lower_bound of the boundary's first
+//                            doc id in the term's posting list (two levels: every 16th boundary by a
+//                            search over the whole list, the others inside the bracketing pair).
+//                            The document axis is cut into slices of kBsSlice docs; with the cursor
+//                            table every (query, slice) is an independent, exactly-known set of
+//                            posting ranges.
+//   bm25_slice_kernel        A WARP owns a run of consecutive slices of one query and works alone:
+//                            no block barrier, no atomics on the accumulators.  The slice's
+//                            accumulators (kBsSlice fp32) live in the warp's shared memory.  The
+//                            posting ranges of the slice are cut into slots (<= 32 postings: one per
+//                            lane; otherwise 128 postings, four per lane with 16-byte loads); the
+//                            warp loads kBsBatch slots at once (all loads in flight before the first
+//                            use), then applies them in term order with plain shared-memory
+//                            read-modify-writes: doc ids inside one posting list are unique, terms
+//                            follow each other in program order, so the fp32 summation order is
+//                            fixed and results are deterministic.  A doc whose running score reaches
+//                            the running threshold is pushed to a small hot list; at the end of a
+//                            slice only the listed docs become candidates (warp-private key buffer,
+//                            bitonic compaction; thresholds shared through the CTA and, per query,
+//                            through global memory) and the accumulators are cleared with one sweep.
 #pragma once
 #include "common.cuh"
 #include "dense_exact.cuh"
@@ -34,13 +37,16 @@ namespace hr {
 
 constexpr int kBmMaxTerms = 64;   // raw terms per query
 constexpr int kBmMaxK = 128;      // candidate depth the kernel supports
-constexpr int kBwThreads = 256;
-constexpr int kBwWarps = kBwThreads / 32;
-constexpr int kBwCons = kBwWarps - 1;   // consumer warps; the last warp plans the next window
-constexpr int kBwSlice = 17 * 128;       // docs per consumer warp in the clear / sweep phases
-constexpr int kBwWin = kBwCons * kBwSlice;   // 15232 docs per window (59.5 KB of accumulators: three CTAs per SM)
+constexpr int kBsThreads = 256;
+constexpr int kBsWarps = kBsThreads / 32;
+constexpr int kBsSlice = 15 * 128;   // docs per warp slice (7.5 KB of accumulators)
+constexpr int kBsCoarse = 16;        // slice boundaries per coarse boundary in the cursor plan
+constexpr int kBsSlotCap = 32;       // slot descriptors per round (512 B per warp)
+constexpr int kBsSlotLen = 128;      // postings of a wide slot
+constexpr int kBsBatch = 4;          // slots a warp keeps in flight
+constexpr int kBsHotCap = 64;        // docs that may reach the threshold in one slice before the full sweep takes over
 // dynamic shared memory: accumulators | warp key buffers (2*kcp keys each)
-__host__ __device__ constexpr int bw_smem_bytes(int kcp) { return kBwWin * 4 + kBwWarps * 2 * kcp * 8; }
+__host__ __device__ constexpr int bs_smem_bytes(int kcp) { return kBsWarps * kBsSlice * 4 + kBsWarps * 2 * kcp * 8; }
 
 __global__ void bm25_impact_kernel(const int32_t* __restrict__ post_doc, const int32_t* __restrict__ post_tf,
                                    const int32_t* __restrict__ doc_len, int64_t nnz, double k1, double b,
@@ -129,25 +135,34 @@ bm25_plan_terms_kernel(const int64_t* __restrict__ indptr, const float* __restri
 }
 
 // ---- plan, step 2: cursor table --------------------------------------------------------------------
-// cur[(size_t)q_indptr[q] * (nwin + 1) + j * nt + u] = number of postings of term u with doc < j * kBwWin.
-// Thread = boundary j (consecutive threads search consecutive boundaries of the same list, so the upper
-// levels of the binary searches share cache lines), looping over the query's terms.
+// cur[(size_t)q_indptr[q] * nb + j * nt + u] = number of postings of term u with doc < j * bdocs, for the nb
+// boundaries j = 0..nb-1 (the last one is the end of the list).  Thread = boundary j (consecutive threads
+// search consecutive boundaries of the same list, so the searches share cache lines), looping over the
+// query's terms.  With `coarse` != nullptr the search runs inside [coarse[j / ratio], coarse[j / ratio + 1]]
+// (a table of the same layout with nbc boundaries every ratio * bdocs docs).
 __global__ void __launch_bounds__(256)
 bm25_plan_cursors_kernel(const int32_t* __restrict__ post_doc, const int32_t* __restrict__ q_indptr,
                          const int* __restrict__ plan_nt, const int64_t* __restrict__ plan_start,
-                         const uint32_t* __restrict__ plan_len, int64_t nwin, uint32_t* __restrict__ cur) {
+                         const uint32_t* __restrict__ plan_len, int64_t nb, int64_t bdocs,
+                         const uint32_t* __restrict__ coarse, int64_t nbc, int ratio, uint32_t* __restrict__ cur) {
   const int q = blockIdx.x;
   const int nt = plan_nt[q];
   const int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-  if (j > nwin || nt == 0) return;
+  if (j >= nb || nt == 0) return;
   const int qa = q_indptr[q];
-  uint32_t* out = cur + (size_t)qa * (size_t)(nwin + 1) + (size_t)j * nt;
-  const int64_t bound64 = j * (int64_t)kBwWin;
+  uint32_t* out = cur + (size_t)qa * (size_t)nb + (size_t)j * nt;
+  const int64_t bound64 = j * bdocs;
+  const uint32_t* cq = coarse ? coarse + (size_t)qa * (size_t)nbc : nullptr;
+  const int64_t jc = j / ratio;
   for (int u = 0; u < nt; ++u) {
     const uint32_t len = plan_len[qa + u];
     uint32_t lo = 0, hi = len;
-    if (j == 0) hi = 0;
-    else if (j == nwin || bound64 > 0x7FFFFFFFll) lo = len;
+    if (cq) {
+      lo = cq[(size_t)jc * nt + u];
+      hi = (jc + 1 < nbc) ? cq[(size_t)(jc + 1) * nt + u] : len;
+    }
+    if (j == 0) hi = lo = 0;
+    else if (j == nb - 1 || bound64 > 0x7FFFFFFFll) lo = hi = len;
     else {
       const int32_t* p = post_doc + plan_start[qa + u];
       const int32_t bound = (int32_t)bound64;
@@ -161,122 +176,115 @@ bm25_plan_cursors_kernel(const int32_t* __restrict__ post_doc, const int32_t* __
 }
 
 // ---- scoring ---------------------------------------------------------------------------------------
-constexpr int kBwSlotCap = 128;   // slot descriptors staged per round (2 KB)
-constexpr int kBwSlotLen = 128;   // postings per slot: one warp, four consecutive postings per lane (16-byte loads)
-constexpr int kBwBatch = 4;       // slots a warp keeps in flight (4 x 2 x 512 B)
-constexpr int kBwHotCap = 1024;   // docs that may reach the threshold in one window before the full sweep takes over
-
-// One slot = kBwSlotLen consecutive postings of one term, starting at a 4-aligned global posting index;
-// [f, e) of them lie inside the current window's range of that term.  Slot g of a round is applied by
-// consumer warp g % 7.  Slots are ordered by term; `need` counts the term boundaries before the slot inside its
-// round: a warp passes that many consumer barriers before it applies the slot, so postings of different
-// terms never race on a document (inside one term doc ids are unique).
-struct __align__(16) BwSlot {
-  uint32_t p_lo, p_hi;   // global posting index of the slot's first posting (multiple of 4)
-  uint32_t meta;         // f | e << 8 | need << 16
+// One slot = consecutive postings of one term inside the current slice.
+//   narrow: e <= 32 postings starting at p, lane l takes posting l (4-byte loads)
+//   wide  : kBsSlotLen postings starting at the 4-aligned index p, lane l takes 4l..4l+3 (16-byte loads);
+//           [f, e) of them lie inside the slice's range of the term
+struct __align__(16) BsSlot {
+  uint32_t p_lo, p_hi;   // global posting index of the slot's first posting
+  uint32_t meta;         // f | e << 8 | narrow << 16 | first slot of its term << 17
   float w;               // term weight (multiplicity * idf)
 };
 
-// Per-term state of a query, kept in the registers of warp 0: lane l owns terms l and l + 32.
-struct BwTerms {
+// Per-term state of a query in the registers of the warp: lane l owns terms l and l + 32.
+struct BsTerms {
   int64_t start[2];        // first posting of the list
   float wgt[2];
-  uint32_t b0[2], b1[2], b2[2];   // cursors at the boundaries of window k, k+1, k+2 (k = current window)
+  uint32_t c0[2], c1[2];   // cursors at the two boundaries of the current slice
 };
 
-// Warp 0: describe slots [r0, r0 + kBwSlotCap) of the window with cursors [lo, hi) per term (r0 < number of
-// slots, or the window is empty).  Slot numbers come from warp prefix sums.  meta[0] = slots in the window,
-// meta[1] = barriers the round needs in total.  With prefetch != 0 the posting ranges are also requested
-// into L2 (one bulk prefetch per array and term).
-__device__ __forceinline__ void bw_build_slots(int lane, const BwTerms& T, const uint32_t (&lo)[2], const uint32_t (&hi)[2],
-                                               int r0, BwSlot* slots, int* meta, const int32_t* post_doc,
-                                               const float* post_imp, bool prefetch) {
-  int64_t a[2];
-  uint32_t n[2];
-  int cnt[2];
+// Warp-collective: describe slots [r0, r0 + kBsSlotCap) of the slice with cursors [c0, c1) per term.
+// Returns the number of slots of the slice.  Slot numbers come from warp prefix sums; each lane then
+// takes one slot of the round and finds the owning term by a binary search over the lanes' prefix sums.
+template <bool TWO_HALVES>
+__device__ __forceinline__ int bs_build_slots(int lane, const BsTerms& T, int r0, BsSlot* slots) {
+  int64_t a[2] = {0, 0};
+  uint32_t n[2] = {0, 0};
+  int cnt[2] = {0, 0};
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    n[half] = hi[half] - lo[half];
-    a[half] = T.start[half] + lo[half];
-    cnt[half] = n[half] ? (int)((a[half] + n[half] - (a[half] & ~(int64_t)3) + kBwSlotLen - 1) / kBwSlotLen) : 0;
-    if (prefetch && n[half]) {
-      const int64_t s0 = a[half] & ~(int64_t)3;
-      const uint32_t bytes = (uint32_t)(((a[half] + n[half] - s0 + 3) & ~(int64_t)3) * 4);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(post_doc + s0), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(post_imp + s0), "r"(bytes) : "memory");
-    }
+  for (int half = 0; half < (TWO_HALVES ? 2 : 1); ++half) {
+    n[half] = T.c1[half] - T.c0[half];
+    a[half] = T.start[half] + T.c0[half];
+    if (n[half] > 32u) cnt[half] = (int)((a[half] + n[half] - (a[half] & ~(int64_t)3) + kBsSlotLen - 1) / kBsSlotLen);
+    else cnt[half] = n[half] ? 1 : 0;
   }
   int iA = cnt[0], iB = cnt[1];
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int va = __shfl_up_sync(0xffffffffu, iA, o), vb = __shfl_up_sync(0xffffffffu, iB, o);
-    if (lane >= o) {
-      iA += va;
-      iB += vb;
+    const int va = __shfl_up_sync(0xffffffffu, iA, o);
+    if (lane >= o) iA += va;
+    if (TWO_HALVES) {
+      const int vb = __shfl_up_sync(0xffffffffu, iB, o);
+      if (lane >= o) iB += vb;
     }
   }
-  const int totA = __shfl_sync(0xffffffffu, iA, 31), totB = __shfl_sync(0xffffffffu, iB, 31);
+  const int totA = __shfl_sync(0xffffffffu, iA, 31);
+  const int totB = TWO_HALVES ? __shfl_sync(0xffffffffu, iB, 31) : 0;
   const int nslots = totA + totB;
-  const int off[2] = {iA - cnt[0], totA + iB - cnt[1]};
-  const unsigned neA = __ballot_sync(0xffffffffu, cnt[0] > 0), neB = __ballot_sync(0xffffffffu, cnt[1] > 0);
-  const unsigned lt = (1u << lane) - 1u;
-  const int rank[2] = {__popc(neA & lt), __popc(neA) + __popc(neB & lt)};
-  // rank of the term that owns slot r0
-  const unsigned inA = __ballot_sync(0xffffffffu, cnt[0] > 0 && off[0] <= r0 && r0 < off[0] + cnt[0]);
-  const unsigned inB = __ballot_sync(0xffffffffu, cnt[1] > 0 && off[1] <= r0 && r0 < off[1] + cnt[1]);
-  int rank0 = 0;
-  if (inA) rank0 = __shfl_sync(0xffffffffu, rank[0], __ffs(inA) - 1);
-  else if (inB) rank0 = __shfl_sync(0xffffffffu, rank[1], __ffs(inB) - 1);
-  const int last = min(nslots, r0 + kBwSlotCap) - 1;
-  if (lane == 0) {
-    meta[0] = nslots;
-    if (nslots == 0) meta[1] = 0;
-  }
-  // slot-parallel: lane takes slots r0 + lane, r0 + lane + 32, ...; the owning term is found by a binary
-  // search over the lanes' inclusive slot prefix sums (shuffles), then its data is fetched from that lane
   const int incl[2] = {iA, totA + iB};
-  for (int g0 = r0; g0 <= last; g0 += 32) {
-    const int gg = g0 + lane;
-    const int half = gg >= totA ? 1 : 0;
-    int lo_l = 0, hi_l = 31;   // smallest lane whose inclusive prefix exceeds gg
+  const int gg = r0 + lane;
+  const int half = (TWO_HALVES && gg >= totA) ? 1 : 0;
+  int lo_l = 0, hi_l = 31;   // smallest lane whose inclusive prefix exceeds gg
 #pragma unroll
-    for (int it = 0; it < 5; ++it) {
-      const int mid = (lo_l + hi_l) >> 1;
-      const int v0 = __shfl_sync(0xffffffffu, incl[0], mid), v1 = __shfl_sync(0xffffffffu, incl[1], mid);
-      if ((half ? v1 : v0) > gg) hi_l = mid; else lo_l = mid + 1;
+  for (int it = 0; it < 5; ++it) {
+    const int mid = (lo_l + hi_l) >> 1;
+    const int v0 = __shfl_sync(0xffffffffu, incl[0], mid);
+    int v = v0;
+    if (TWO_HALVES) {
+      const int v1 = __shfl_sync(0xffffffffu, incl[1], mid);
+      v = half ? v1 : v0;
     }
-    const int src = lo_l;
-    const int64_t a0 = __shfl_sync(0xffffffffu, a[0], src), a1 = __shfl_sync(0xffffffffu, a[1], src);
-    const uint32_t n0 = __shfl_sync(0xffffffffu, n[0], src), n1 = __shfl_sync(0xffffffffu, n[1], src);
-    const int o0 = __shfl_sync(0xffffffffu, off[0], src), o1 = __shfl_sync(0xffffffffu, off[1], src);
-    const int r_0 = __shfl_sync(0xffffffffu, rank[0], src), r_1 = __shfl_sync(0xffffffffu, rank[1], src);
-    const float w0 = __shfl_sync(0xffffffffu, T.wgt[0], src), w1 = __shfl_sync(0xffffffffu, T.wgt[1], src);
-    if (gg <= last) {
-      const int64_t at = half ? a1 : a0;
-      const int64_t s0 = at & ~(int64_t)3;
-      const int64_t end = at + (half ? n1 : n0);
-      const int sl = gg - (half ? o1 : o0);
-      const int64_t ps = s0 + (int64_t)sl * kBwSlotLen;
-      const uint32_t need = (uint32_t)max((half ? r_1 : r_0) - rank0, 0);
-      const uint32_t f = sl == 0 ? (uint32_t)(at - s0) : 0u;
-      const uint32_t e = (uint32_t)min((int64_t)kBwSlotLen, end - ps);
-      BwSlot d;
-      d.p_lo = (uint32_t)ps;
-      d.p_hi = (uint32_t)(ps >> 32);
-      d.meta = f | (e << 8) | (need << 16);
-      d.w = half ? w1 : w0;
-      slots[gg - r0] = d;
-      if (gg == last) meta[1] = (int)need;
+    if (v > gg) hi_l = mid; else lo_l = mid + 1;
+  }
+  const int src = lo_l;
+  int64_t at = __shfl_sync(0xffffffffu, a[0], src);
+  uint32_t nn = __shfl_sync(0xffffffffu, n[0], src);
+  int inc = __shfl_sync(0xffffffffu, incl[0], src);
+  int cn = __shfl_sync(0xffffffffu, cnt[0], src);
+  float wt = __shfl_sync(0xffffffffu, T.wgt[0], src);
+  if (TWO_HALVES) {
+    const int64_t a1 = __shfl_sync(0xffffffffu, a[1], src);
+    const uint32_t n1 = __shfl_sync(0xffffffffu, n[1], src);
+    const int i1 = __shfl_sync(0xffffffffu, incl[1], src);
+    const int c1 = __shfl_sync(0xffffffffu, cnt[1], src);
+    const float w1 = __shfl_sync(0xffffffffu, T.wgt[1], src);
+    if (half) {
+      at = a1;
+      nn = n1;
+      inc = i1;
+      cn = c1;
+      wt = w1;
     }
   }
+  if (gg < nslots) {
+    const int sl = gg - (inc - cn);   // slot index inside its term
+    BsSlot d;
+    int64_t ps;
+    uint32_t f, e, narrow;
+    if (nn <= 32u) {
+      ps = at;
+      f = 0;
+      e = nn;
+      narrow = 1;
+    } else {
+      const int64_t s0 = at & ~(int64_t)3;
+      ps = s0 + (int64_t)sl * kBsSlotLen;
+      f = sl == 0 ? (uint32_t)(at - s0) : 0u;
+      e = (uint32_t)min((int64_t)kBsSlotLen, at + nn - ps);
+      narrow = 0;
+    }
+    d.p_lo = (uint32_t)ps;
+    d.p_hi = (uint32_t)(ps >> 32);
+    d.meta = f | (e << 8) | (narrow << 16) | ((sl == 0 ? 1u : 0u) << 17);
+    d.w = wt;
+    slots[lane] = d;
+  }
+  return nslots;
 }
-
-// barrier 1: the consumer warps only (the planner warp never takes part in a term boundary)
-__device__ __forceinline__ void bw_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kBwCons * 32) : "memory"); }
 
 // Warp-collective append of a candidate key to the warp's key buffer (compaction by bitonic sort keeps the
 // best kc and raises the warp / CTA / query thresholds).
-__device__ __forceinline__ void bw_append(bool take, unsigned long long key, uint64_t* cb, int& cbn, int cbcap, int kc,
+__device__ __forceinline__ void bs_append(bool take, unsigned long long key, uint64_t* cb, int& cbn, int cbcap, int kc,
                                           unsigned long long& tau, float& tau_f, int lane,
                                           unsigned long long* s_tau, unsigned long long* tau_gq) {
   const unsigned m = __ballot_sync(0xffffffffu, take);
@@ -305,23 +313,197 @@ __device__ __forceinline__ void bw_append(bool take, unsigned long long key, uin
 }
 
 // grid = (nq, S): query fastest, so the first wave holds span 0 of many queries and later spans start
-// from the thresholds earlier spans published in tau_g.  out_keys [nq][S][kc], out_n [nq][S].
+// from the thresholds earlier spans published in tau_g.  CTA (q, g) covers slices [g*spc, (g+1)*spc), its
+// warp w the sub-run [w*spw, (w+1)*spw) of that.  out_keys [nq][S][kc], out_n [nq][S].
 // kcp = power of two >= max(kc, 32); a warp's key buffer holds 2*kcp keys.
-__global__ void __launch_bounds__(kBwThreads, 3)
-bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict__ post_imp,
-                   const int32_t* __restrict__ q_indptr, const int* __restrict__ plan_nt,
-                   const int64_t* __restrict__ plan_start, const float* __restrict__ plan_wgt,
-                   const uint32_t* __restrict__ plan_cur, int64_t nwin, int wpc, int S, int kc, int kcp,
-                   uint64_t* __restrict__ out_keys, int* __restrict__ out_n, unsigned long long* __restrict__ tau_g, int flags) {
+template <bool TWO_HALVES>
+__device__ __forceinline__ void bs_warp_run(const int32_t* __restrict__ post_doc, const float* __restrict__ post_imp,
+                                            const uint32_t* __restrict__ curq, int nt, int64_t nsl, int64_t s_begin,
+                                            int64_t s_end, BsTerms& T, float* acc, BsSlot* slots, uint16_t* hotl,
+                                            uint64_t* cb, int& cbn, int cbcap, int kc, unsigned long long& tau,
+                                            float& tau_f, unsigned long long* s_tau, unsigned long long* tau_gq,
+                                            int lane) {
+  constexpr int NH = TWO_HALVES ? 2 : 1;
+  uint32_t nxt[2] = {0, 0};
+  for (int64_t sidx = s_begin; sidx < s_end; ++sidx) {
+    const int32_t docbase = (int32_t)(sidx * kBsSlice);
+    // cursors of the boundary after the next slice; postings of the next slice towards L2
+#pragma unroll
+    for (int half = 0; half < NH; ++half) {
+      const int term = lane + 32 * half;
+      nxt[half] = T.c1[half];
+      if (term < nt && sidx + 2 <= nsl) nxt[half] = __ldg(curq + (size_t)(sidx + 2) * nt + term);
+    }
+    unsigned long long gt = 0;
+    if ((sidx & 7) == 0 && lane == 0) gt = *((volatile unsigned long long*)tau_gq);
+    const float tau_pos = tau_f > 0.f ? tau_f : 1.4e-45f;   // x >= tau_pos <=> x > 0 && x >= tau_f
+    int nhot = 0;   // warp-uniform
+    __syncwarp();
+    const int nslots = bs_build_slots<TWO_HALVES>(lane, T, 0, slots);
+    __syncwarp();
+    for (int r0 = 0; r0 < nslots; r0 += kBsSlotCap) {
+      if (r0 > 0) {
+        __syncwarp();
+        bs_build_slots<TWO_HALVES>(lane, T, r0, slots);
+        __syncwarp();
+      }
+      const int nr = min(kBsSlotCap, nslots - r0);
+      for (int b0 = 0; b0 < nr; b0 += kBsBatch) {
+        int4 dd[kBsBatch];
+        float4 vv[kBsBatch];
+        uint32_t meta[kBsBatch];
+        float ww[kBsBatch];
+#pragma unroll
+        for (int j = 0; j < kBsBatch; ++j) {
+          meta[j] = 0;
+          ww[j] = 0.f;
+          dd[j] = make_int4(0, 0, 0, 0);
+          vv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b0 + j < nr) {
+            const BsSlot e = slots[b0 + j];
+            meta[j] = e.meta;
+            ww[j] = e.w;
+            const int64_t p = (int64_t)(((uint64_t)e.p_hi << 32) | e.p_lo);
+            const uint32_t en = (e.meta >> 8) & 0xFFu;
+            if (e.meta & 0x10000u) {
+              if ((uint32_t)lane < en) {
+                dd[j].x = __ldg(post_doc + p + lane);
+                vv[j].x = __ldg(post_imp + p + lane);
+              }
+            } else if ((uint32_t)(4 * lane) < en) {
+              dd[j] = __ldg(reinterpret_cast<const int4*>(post_doc + p + 4 * lane));
+              vv[j] = __ldg(reinterpret_cast<const float4*>(post_imp + p + 4 * lane));
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kBsBatch; ++j) {
+          if (b0 + j < nr) {   // warp-uniform
+            const uint32_t f = meta[j] & 0xFFu, e = (meta[j] >> 8) & 0xFFu;
+            if (meta[j] & 0x20000u) __syncwarp();   // a new term may touch docs of the previous one
+            float xs[4] = {0.f, 0.f, 0.f, 0.f};
+            int offs[4] = {0, 0, 0, 0};
+            if (meta[j] & 0x10000u) {
+              // narrow: one posting per lane
+              const bool valid = (uint32_t)lane < e;
+              offs[0] = valid ? dd[j].x - docbase : 0;
+              if (valid) {
+                xs[0] = fmaf(ww[j], vv[j].x, acc[offs[0]]);
+                acc[offs[0]] = xs[0];
+              }
+            } else {
+              const int dv[4] = {dd[j].x, dd[j].y, dd[j].z, dd[j].w};
+              const float iv[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
+              bool valid[4];
+              // the four docs of a lane are distinct (one posting list): read all, then add, then write
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const uint32_t idx = 4u * lane + e4;
+                valid[e4] = idx >= f && idx < e;
+                offs[e4] = valid[e4] ? dv[e4] - docbase : 0;
+                xs[e4] = acc[offs[e4]];
+              }
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                xs[e4] = valid[e4] ? fmaf(ww[j], iv[e4], xs[e4]) : 0.f;
+                if (valid[e4]) acc[offs[e4]] = xs[e4];
+              }
+            }
+            // docs whose running score reached the threshold go to the hot list (the lane applying a doc's
+            // last posting sees its final score, so every candidate is listed at least once)
+            const bool hot = fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3])) >= tau_pos;
+            if (__any_sync(0xffffffffu, hot)) {
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const bool h = xs[e4] >= tau_pos;
+                const unsigned hm = __ballot_sync(0xffffffffu, h);
+                if (hm) {
+                  if (h) {
+                    const int pos = nhot + __popc(hm & ((1u << lane) - 1u));
+                    if (pos < kBsHotCap) hotl[pos] = (uint16_t)offs[e4];
+                  }
+                  nhot += __popc(hm);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- end of slice ----
+    {
+      unsigned long long ct = *((volatile unsigned long long*)s_tau);
+      const unsigned long long g0 = __shfl_sync(0xffffffffu, gt, 0);
+      if (g0 > ct) ct = g0;
+      if (ct > tau) {
+        tau = ct;
+        tau_f = key_score(tau);
+      }
+    }
+    if (nhot > kBsHotCap) {
+      // cold thresholds: sweep the slice, extract and clear
+#pragma unroll 2
+      for (int j = lane * 4; j < kBsSlice; j += 128) {
+        float4 v = *reinterpret_cast<float4*>(acc + j);
+        const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        *reinterpret_cast<float4*>(acc + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (__any_sync(0xffffffffu, mx > 0.f && mx >= tau_f)) {
+          const float ve[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            unsigned long long key = 0;
+            bool take = false;
+            if (ve[e4] > 0.f && ve[e4] >= tau_f) {
+              key = make_key(ve[e4], (uint32_t)(docbase + j + e4));
+              take = key > tau;
+            }
+            bs_append(take, key, cb, cbn, cbcap, kc, tau, tau_f, lane, s_tau, tau_gq);
+          }
+        }
+      }
+    } else {
+      // the listed docs only: the first reader of a doc takes its score (exchange with 0), duplicates see 0
+      for (int i0 = 0; i0 < nhot; i0 += 32) {
+        const int i = i0 + lane;
+        unsigned long long key = 0;
+        bool take = false;
+        if (i < nhot) {
+          const int off = hotl[i];
+          const float v = atomicExch(acc + off, 0.f);
+          if (v > 0.f && v >= tau_f) {
+            key = make_key(v, (uint32_t)(docbase + off));
+            take = key > tau;
+          }
+        }
+        bs_append(take, key, cb, cbn, cbcap, kc, tau, tau_f, lane, s_tau, tau_gq);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = lane * 4; j < kBsSlice; j += 128) *reinterpret_cast<float4*>(acc + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // advance the cursors by one slice
+#pragma unroll
+    for (int half = 0; half < NH; ++half) {
+      T.c0[half] = T.c1[half];
+      T.c1[half] = nxt[half];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBsThreads, 3)
+bm25_slice_kernel(const int32_t* __restrict__ post_doc, const float* __restrict__ post_imp,
+                  const int32_t* __restrict__ q_indptr, const int* __restrict__ plan_nt,
+                  const int64_t* __restrict__ plan_start, const float* __restrict__ plan_wgt,
+                  const uint32_t* __restrict__ plan_cur, int64_t nsl, int spc, int S, int kc, int kcp,
+                  uint64_t* __restrict__ out_keys, int* __restrict__ out_n, unsigned long long* __restrict__ tau_g) {
   extern __shared__ __align__(16) uint8_t bsm[];
-  float* acc = (float*)bsm;
-  uint64_t* cb_all = (uint64_t*)(bsm + kBwWin * 4);
-  __shared__ BwSlot s_slots[2][kBwSlotCap];   // double buffered: warp 0 describes window k+1 during window k
-  __shared__ int s_meta[2][2];
-  __shared__ uint16_t s_hot[kBwHotCap];
+  float* acc_all = (float*)bsm;
+  uint64_t* cb_all = (uint64_t*)(bsm + kBsWarps * kBsSlice * 4);
+  __shared__ BsSlot s_slots[kBsWarps][kBsSlotCap];
+  __shared__ uint16_t s_hot[kBsWarps][kBsHotCap];
   __shared__ unsigned long long s_tau;
-  __shared__ unsigned int s_nhot[2];
-  __shared__ int s_wn[kBwWarps];
+  __shared__ int s_wn[kBsWarps];
 
   const int q = blockIdx.x;
   const int g = blockIdx.y;
@@ -331,230 +513,47 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
   uint64_t* cb = cb_all + (size_t)w * 2 * kcp;
   const int cbcap = 2 * kcp;
   const int nt = plan_nt[q];
-  const int64_t win0 = (int64_t)g * wpc;
-  const int64_t win1 = min(nwin, win0 + wpc);
-  if (nt == 0 || win0 >= win1) {   // uniform
+  const int64_t cta0 = (int64_t)g * spc;
+  const int64_t cta1 = min(nsl, cta0 + spc);
+  if (nt == 0 || cta0 >= cta1) {   // uniform
     if (tid == 0) out_n[(size_t)q * S + g] = 0;
     return;
   }
+  const int64_t spw = (cta1 - cta0 + kBsWarps - 1) / kBsWarps;
+  const int64_t s_begin = min(cta1, cta0 + (int64_t)w * spw);
+  const int64_t s_end = min(cta1, s_begin + spw);
   const int qa = q_indptr[q];
-  const uint32_t* curq = plan_cur + (size_t)qa * (size_t)(nwin + 1);
+  const uint32_t* curq = plan_cur + (size_t)qa * (size_t)(nsl + 1);
   unsigned long long* tau_gq = tau_g + q;
-  BwTerms T;
-  uint32_t nxt[2] = {0, 0};   // cursors at boundary k+3, in flight during window k
+  float* acc = acc_all + w * kBsSlice;
+  BsTerms T;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int term = lane + 32 * half;
     T.start[half] = 0;
     T.wgt[half] = 0.f;
-    T.b0[half] = T.b1[half] = T.b2[half] = 0;
-    if (w == kBwCons && term < nt) {
+    T.c0[half] = T.c1[half] = 0;
+    if (term < nt && s_begin < s_end) {
       T.start[half] = plan_start[qa + term];
       T.wgt[half] = plan_wgt[qa + term];
-      T.b0[half] = curq[(size_t)win0 * nt + term];
-      T.b1[half] = curq[(size_t)(win0 + 1) * nt + term];
-      T.b2[half] = win0 + 2 <= nwin ? curq[(size_t)(win0 + 2) * nt + term] : T.b1[half];
+      T.c0[half] = curq[(size_t)s_begin * nt + term];
+      T.c1[half] = curq[(size_t)(s_begin + 1) * nt + term];
     }
   }
-  if (tid == 0) {
-    s_tau = *((volatile unsigned long long*)tau_gq);
-    s_nhot[0] = 0;
-    s_nhot[1] = 0;
-  }
-  for (int i = tid * 4; i < kBwWin; i += kBwThreads * 4) *reinterpret_cast<float4*>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool planner = w == kBwCons;
-  if (planner) bw_build_slots(lane, T, T.b0, T.b1, 0, s_slots[win0 & 1], s_meta[win0 & 1], post_doc, post_imp, false);
+  if (tid == 0) s_tau = *((volatile unsigned long long*)tau_gq);
+#pragma unroll
+  for (int j = lane * 4; j < kBsSlice; j += 128) *reinterpret_cast<float4*>(acc + j) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
   int cbn = 0;                 // keys in this warp's buffer (warp-uniform)
   unsigned long long tau = 0;  // this warp's threshold key: a lower bound of the query's kc-th best
   float tau_f = 0.f;
-  float* slice = acc + (planner ? 0 : w) * kBwSlice;
-  // one batch of slots per warp in registers
-  int4 dd[kBwBatch];
-  float4 vv[kBwBatch];
-  uint32_t meta[kBwBatch];
-  float ww[kBwBatch];
-  auto load_batch = [&](const BwSlot* tab, int nr, int b0) {
-#pragma unroll
-    for (int j = 0; j < kBwBatch; ++j) {
-      const int gr = b0 + w + kBwCons * j;
-      meta[j] = 0;
-      ww[j] = 0.f;
-      dd[j] = make_int4(0, 0, 0, 0);
-      vv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr < nr) {
-        const BwSlot e = tab[gr];
-        meta[j] = e.meta;
-        ww[j] = e.w;
-        if ((uint32_t)(4 * lane) < ((e.meta >> 8) & 0xFFu)) {
-          const int64_t p = (int64_t)(((uint64_t)e.p_hi << 32) | e.p_lo) + 4 * lane;
-          dd[j] = __ldg(reinterpret_cast<const int4*>(post_doc + p));
-          vv[j] = __ldg(reinterpret_cast<const float4*>(post_imp + p));
-        }
-      }
-    }
-  };
-  if (!planner) load_batch(s_slots[win0 & 1], min(kBwSlotCap, s_meta[win0 & 1][0]), 0);
-  for (int64_t win = win0; win < win1; ++win) {
-    const int32_t docbase = (int32_t)(win * kBwWin);
-    const int buf = (int)(win & 1);
-    unsigned int* nhot_p = &s_nhot[buf];
-    unsigned long long gt = 0;
-    if (planner) {
-      if (lane == 0) gt = *((volatile unsigned long long*)tau_gq);
-      // cursors three boundaries ahead; slots of the next window (its postings go to L2 meanwhile)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int term = lane + 32 * half;
-        nxt[half] = T.b2[half];
-        if (term < nt && win + 3 <= nwin) nxt[half] = __ldg(curq + (size_t)(win + 3) * nt + term);
-      }
-      if (win + 1 < win1)
-        bw_build_slots(lane, T, T.b1, T.b2, 0, s_slots[buf ^ 1], s_meta[buf ^ 1], post_doc, post_imp, !(flags & 1));
-    }
-    // ---- apply: slot g of a round belongs to warp g % 8; kBwBatch slots in flight per warp ----
-    const float tau_pos = tau_f > 0.f ? tau_f : 1.4e-45f;   // x >= tau_pos <=> x > 0 && x >= tau_f
-    const int nslots = s_meta[buf][0];
-    for (int r0 = 0; r0 < nslots; r0 += kBwSlotCap) {
-      if (r0 > 0) {   // more slots than the staging table holds: describe the next round
-        __syncthreads();
-        if (planner) bw_build_slots(lane, T, T.b0, T.b1, r0, s_slots[buf], s_meta[buf], post_doc, post_imp, false);
-        __syncthreads();
-      }
-      const int nr = min(kBwSlotCap, nslots - r0);
-      const int total_need = s_meta[buf][1];
-      if (planner) continue;
-      int done = 0;   // barriers this warp has passed in this round
-      for (int b0 = 0; b0 < nr; b0 += kBwCons * kBwBatch) {
-        if (r0 + b0 > 0 || ((flags & 2) && win > win0)) load_batch(s_slots[buf], nr, b0);   // the window's first batch is already in flight
-#pragma unroll
-        for (int j = 0; j < kBwBatch; ++j) {
-          const int gr = b0 + w + kBwCons * j;
-          if (gr < nr) {   // warp-uniform
-            const int need = (int)(meta[j] >> 16);
-            while (done < need) {
-              bw_barrier();
-              ++done;
-            }
-            const uint32_t f = meta[j] & 0xFFu, e = (meta[j] >> 8) & 0xFFu;
-            const int dv[4] = {dd[j].x, dd[j].y, dd[j].z, dd[j].w};
-            const float iv[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
-            float xs[4];
-            int offs[4];
-            bool valid[4];
-            bool hot = false;
-            // the four docs of a lane are distinct (one posting list): read all, then add, then write
-#pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) {
-              const uint32_t idx = 4u * lane + e4;
-              valid[e4] = idx >= f && idx < e;
-              offs[e4] = valid[e4] ? dv[e4] - docbase : 0;
-              xs[e4] = acc[offs[e4]];
-            }
-#pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) {
-              xs[e4] = valid[e4] ? fmaf(ww[j], iv[e4], xs[e4]) : 0.f;
-              if (valid[e4]) acc[offs[e4]] = xs[e4];
-              hot = hot || xs[e4] >= tau_pos;
-            }
-            // docs whose running score reached the threshold go to the hot list (the thread applying a doc's
-            // last posting sees its final score, so every candidate is listed at least once)
-            if (__any_sync(0xffffffffu, hot)) {
-#pragma unroll
-              for (int e4 = 0; e4 < 4; ++e4) {
-                const bool h = xs[e4] >= tau_pos;
-                const unsigned hm = __ballot_sync(0xffffffffu, h);
-                if (hm) {
-                  unsigned base = 0;
-                  const int leader = __ffs(hm) - 1;
-                  if (lane == leader) base = atomicAdd(nhot_p, (unsigned)__popc(hm));
-                  base = __shfl_sync(0xffffffffu, base, leader);
-                  if (h) {
-                    const unsigned pos = base + __popc(hm & ((1u << lane) - 1u));
-                    if (pos < kBwHotCap) s_hot[pos] = (uint16_t)offs[e4];
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
-      while (done < total_need) {   // warps without slots behind the last term boundary catch up
-        bw_barrier();
-        ++done;
-      }
-    }
-    // ---- end of window ----
-    if (planner && lane == 0 && gt > s_tau) s_tau = gt;   // elsewhere s_tau only changes by atomicMax after the next barrier
-    __syncthreads();
-    // the next window's first batch of postings starts its trip now (its slots were described during this window)
-    if (!planner && win + 1 < win1 && !(flags & 2)) load_batch(s_slots[buf ^ 1], min(kBwSlotCap, s_meta[buf ^ 1][0]), 0);
-    const unsigned nhot = *((volatile unsigned int*)nhot_p);
-    {
-      const unsigned long long ct = *((volatile unsigned long long*)&s_tau);
-      if (ct > tau) {
-        tau = ct;
-        tau_f = key_score(tau);
-      }
-    }
-    if (nhot > kBwHotCap) {
-      // cold thresholds: sweep the warp's slice, extract and clear
-      const int32_t s0 = docbase + w * kBwSlice;
-#pragma unroll 2
-      for (int j = lane * 4; !planner && j < kBwSlice; j += 128) {
-        float4 v = *reinterpret_cast<float4*>(slice + j);
-        const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-        *reinterpret_cast<float4*>(slice + j) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (__any_sync(0xffffffffu, mx > 0.f && mx >= tau_f)) {
-          const float ve[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            unsigned long long key = 0;
-            bool take = false;
-            if (ve[e4] > 0.f && ve[e4] >= tau_f) {
-              key = make_key(ve[e4], (uint32_t)(s0 + j + e4));
-              take = key > tau;
-            }
-            bw_append(take, key, cb, cbn, cbcap, kc, tau, tau_f, lane, &s_tau, tau_gq);
-          }
-        }
-      }
-    } else {
-      if (nhot > 0) {
-        // the listed docs only: the first reader of a doc takes its score (exchange with 0), duplicates see 0
-        for (unsigned i0 = 0; !planner && i0 < nhot; i0 += kBwCons * 32) {
-          const unsigned i = i0 + tid;
-          unsigned long long key = 0;
-          bool take = false;
-          if (i < nhot) {
-            const int off = s_hot[i];
-            const float v = atomicExch(acc + off, 0.f);
-            if (v > 0.f && v >= tau_f) {
-              key = make_key(v, (uint32_t)(docbase + off));
-              take = key > tau;
-            }
-          }
-          bw_append(take, key, cb, cbn, cbcap, kc, tau, tau_f, lane, &s_tau, tau_gq);
-        }
-        __syncthreads();   // uniform (nhot is): the sweep below must not clear a listed doc before it is read
-      }
-      if (!planner) {
-#pragma unroll
-        for (int j = lane * 4; j < kBwSlice; j += 128) *reinterpret_cast<float4*>(slice + j) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    if (planner) {   // advance the cursors by one window
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        T.b0[half] = T.b1[half];
-        T.b1[half] = T.b2[half];
-        T.b2[half] = nxt[half];
-      }
-      if (lane == 0) s_nhot[buf ^ 1] = 0;
-    }
-    __syncthreads();   // clears visible before the next window's first slot is applied
-  }
+  if (nt <= 32)
+    bs_warp_run<false>(post_doc, post_imp, curq, nt, nsl, s_begin, s_end, T, acc, s_slots[w], s_hot[w], cb, cbn, cbcap,
+                       kc, tau, tau_f, &s_tau, tau_gq, lane);
+  else
+    bs_warp_run<true>(post_doc, post_imp, curq, nt, nsl, s_begin, s_end, T, acc, s_slots[w], s_hot[w], cb, cbn, cbcap,
+                      kc, tau, tau_f, &s_tau, tau_gq, lane);
   // ---- warp list -> sorted top-kc ----
   for (int i = cbn + lane; i < cbcap; i += 32) cb[i] = 0;
   warp_bitonic_desc(cb, cbcap, lane);
@@ -565,18 +564,18 @@ bm25_window_kernel(const int32_t* __restrict__ post_doc, const float* __restrict
   }
   __syncthreads();
   // ---- CTA merge of the warp lists (the accumulator area is the sort buffer) ----
-  uint64_t* mbuf = (uint64_t*)acc;
-  const int total = kBwWarps * kcp;
-  for (int i = tid; i < total; i += kBwThreads) {
+  uint64_t* mbuf = (uint64_t*)acc_all;
+  const int total = kBsWarps * kcp;
+  for (int i = tid; i < total; i += kBsThreads) {
     const int ww = i / kcp, j = i - ww * kcp;
     mbuf[i] = (j < s_wn[ww]) ? cb_all[(size_t)ww * 2 * kcp + j] : 0ull;
   }
   block_bitonic_desc(mbuf, total);
   uint64_t* o = out_keys + ((size_t)q * S + g) * kc;
   int m = 0;
-  for (int ww = 0; ww < kBwWarps; ++ww) m += s_wn[ww];
+  for (int ww = 0; ww < kBsWarps; ++ww) m += s_wn[ww];
   m = min(m, kc);
-  for (int j = tid; j < kc; j += kBwThreads) o[j] = (j < m) ? mbuf[j] : 0ull;
+  for (int j = tid; j < kc; j += kBsThreads) o[j] = (j < m) ? mbuf[j] : 0ull;
   if (tid == 0) out_n[(size_t)q * S + g] = m;
 }
 

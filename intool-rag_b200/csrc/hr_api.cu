@@ -515,7 +515,9 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     const int nb = (int)std::min<int64_t>(kScanNqMax, nq - q0);
     float* Db = D_dev + q0 * k;
     int64_t* Ib = I_dev + q0 * k;
-    const int nbp = std::max(nb, 32);  // query rows materialised for the TMA (zero rows beyond nb)
+    // query rows materialised for the TMA (zero rows beyond nb): a full 128-row box, so that the SMs'
+    // re-reads of a small batch spread over 128 rows instead of hammering a few L2 lines
+    const int nbp = std::max(nb, getenv("HR_QROWS") ? atoi(getenv("HR_QROWS")) : 128);
     HR_TRY(h->qpad.ensure((size_t)nbp * h->ld * 4));
     if (filter_is_bf16(h)) HR_TRY(h->qh.ensure((size_t)nbp * h->ld * 2));
     {
@@ -751,7 +753,7 @@ struct hr_bm25 {
   int32_t* post_doc = nullptr;
   float* post_imp = nullptr;
   float* idf = nullptr;
-  DevBuf keys, ns, io_qi, io_qt, io_S, io_I, touched, plan_nt, plan_start, plan_len, plan_wgt, plan_cur, tau;
+  DevBuf keys, ns, io_qi, io_qt, io_S, io_I, touched, plan_nt, plan_start, plan_len, plan_wgt, plan_cur, plan_coarse, tau;
 };
 
 extern "C" int hr_bm25_destroy(hr_bm25* h) {
@@ -762,7 +764,7 @@ extern "C" int hr_bm25_destroy(hr_bm25* h) {
   if (h->post_imp) cudaFree(h->post_imp);
   if (h->idf) cudaFree(h->idf);
   DevBuf* bufs[] = {&h->keys,    &h->ns,         &h->io_qi,    &h->io_qt,    &h->io_S,     &h->io_I, &h->touched,
-                    &h->plan_nt, &h->plan_start, &h->plan_len, &h->plan_wgt, &h->plan_cur, &h->tau};
+                    &h->plan_nt, &h->plan_start, &h->plan_len, &h->plan_wgt, &h->plan_cur, &h->plan_coarse, &h->tau};
   for (DevBuf* b : bufs) b->release();
   delete h;
   return HR_OK;
@@ -911,22 +913,25 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   }
   int kcp = 32;
   while (kcp < k) kcp <<= 1;
-  const int smem = bw_smem_bytes(kcp);
-  const int64_t nwin = std::max<int64_t>(1, (h->N + kBwWin - 1) / kBwWin);
-  const size_t cur_bytes = (size_t)std::max<int64_t>(n_terms, 1) * (size_t)(nwin + 1) * 4;
-  if (cur_bytes > ((size_t)8 << 30))
-    return set_err(HR_ERR_INVALID, "bm25: query batch too large for the cursor table (split the batch)");
-  // spans per query: ~6 waves of CTAs over the machine (3 resident per SM), bounded by the merge capacity
-  int64_t S = (6 * 3 * (int64_t)h->num_sms + nq - 1) / nq;
-  S = std::max<int64_t>(1, std::min<int64_t>({S, nwin, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
-  const int wpc = (int)((nwin + S - 1) / S);
-  S = (nwin + wpc - 1) / wpc;
+  const int smem = bs_smem_bytes(kcp);
+  const int64_t nsl = std::max<int64_t>(1, (h->N + kBsSlice - 1) / kBsSlice);   // slices; nsl + 1 boundaries
+  const int64_t nbc = (nsl + kBsCoarse - 1) / kBsCoarse + 1;                    // coarse boundaries
   const size_t nterm_slots = (size_t)std::max<int64_t>(n_terms, 1);
+  const size_t cur_bytes = nterm_slots * (size_t)(nsl + 1) * 4;
+  if (cur_bytes > ((size_t)16 << 30))
+    return set_err(HR_ERR_INVALID, "bm25: query batch too large for the cursor table (split the batch)");
+  // spans per query: ~8 waves of CTAs over the machine (3 resident per SM), bounded by the merge capacity;
+  // a CTA wants at least one slice per warp
+  int64_t S = (8 * 3 * (int64_t)h->num_sms + nq - 1) / nq;
+  S = std::max<int64_t>(1, std::min<int64_t>({S, (nsl + kBsWarps - 1) / kBsWarps, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
+  const int spc = (int)((nsl + S - 1) / S);
+  S = (nsl + spc - 1) / spc;
   HR_TRY(h->plan_nt.ensure((size_t)nq * 4));
   HR_TRY(h->plan_start.ensure(nterm_slots * 8));
   HR_TRY(h->plan_len.ensure(nterm_slots * 4));
   HR_TRY(h->plan_wgt.ensure(nterm_slots * 4));
   HR_TRY(h->plan_cur.ensure(cur_bytes));
+  HR_TRY(h->plan_coarse.ensure(nterm_slots * (size_t)nbc * 4));
   HR_TRY(h->tau.ensure((size_t)nq * 8));
   HR_TRY(h->keys.ensure((size_t)nq * S * k * 8));
   HR_TRY(h->ns.ensure((size_t)nq * S * 4));
@@ -936,21 +941,29 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
       h->plan_len.as<uint32_t>(), h->plan_wgt.as<float>(), touched_dev);
   HR_LAUNCHED();
   {
-    dim3 grid((unsigned)nq, (unsigned)((nwin + 1 + 255) / 256));
+    // coarse boundaries (every kBsCoarse slices) by a search over the whole list, then every slice boundary
+    // inside its bracketing coarse pair
+    dim3 gridc((unsigned)nq, (unsigned)((nbc + 255) / 256));
+    bm25_plan_cursors_kernel<<<gridc, 256, 0, st>>>(h->post_doc, qi_dev, h->plan_nt.as<int>(),
+                                                    h->plan_start.as<int64_t>(), h->plan_len.as<uint32_t>(), nbc,
+                                                    (int64_t)kBsSlice * kBsCoarse, nullptr, 0, 1,
+                                                    h->plan_coarse.as<uint32_t>());
+    HR_LAUNCHED();
+    dim3 grid((unsigned)nq, (unsigned)((nsl + 1 + 255) / 256));
     bm25_plan_cursors_kernel<<<grid, 256, 0, st>>>(h->post_doc, qi_dev, h->plan_nt.as<int>(),
-                                                   h->plan_start.as<int64_t>(), h->plan_len.as<uint32_t>(), nwin,
+                                                   h->plan_start.as<int64_t>(), h->plan_len.as<uint32_t>(), nsl + 1,
+                                                   (int64_t)kBsSlice, h->plan_coarse.as<uint32_t>(), nbc, kBsCoarse,
                                                    h->plan_cur.as<uint32_t>());
     HR_LAUNCHED();
   }
-  HR_CUDA(cudaFuncSetAttribute(bm25_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  HR_CUDA(cudaFuncSetAttribute(bm25_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   {
     dim3 grid((unsigned)nq, (unsigned)S);
-    bm25_window_kernel<<<grid, kBwThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
-                                                       h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
-                                                       h->plan_cur.as<uint32_t>(), nwin, wpc, (int)S, k, kcp,
-                                                       h->keys.as<uint64_t>(), h->ns.as<int>(),
-                                                       h->tau.as<unsigned long long>(),
-                                                       getenv("HR_BM25_FLAGS") ? atoi(getenv("HR_BM25_FLAGS")) : 0);
+    bm25_slice_kernel<<<grid, kBsThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
+                                                      h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
+                                                      h->plan_cur.as<uint32_t>(), nsl, spc, (int)S, k, kcp,
+                                                      h->keys.as<uint64_t>(), h->ns.as<int>(),
+                                                      h->tau.as<unsigned long long>());
     HR_LAUNCHED();
   }
   bm25_merge_kernel<<<(unsigned)nq, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), (int)S, k, k, h->id_base,
