@@ -399,7 +399,7 @@ __global__ void iota_kernel(int* a, int n, int base) {
   if (i < n) a[i] = base + i;
 }
 
-constexpr int kSampleStride = 64;  // threshold pre-pass visits every 64th corpus tile
+constexpr int kSampleStrideMax = 1024;  // the threshold pre-pass visits at most every 2nd, at least every 1024th corpus tile
 
 static int list_len_for_k(int k) {
   if (k <= 16) return 32;
@@ -585,9 +585,13 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     //      seeds tau_g: about KLs*stride (= 4*KL) corpus rows beat it, so in the main pass only a handful
     //      of scores per CTA pass the threshold and no per-CTA list ever fills.  Correctness never depends
     //      on the seed: the certificate in rescore_finalize compares against the final threshold. ----
-    const int stride = std::max(1, std::min(kSampleStride, num_ctiles / 8));
+    // Sample size: two tiles per scheduling unit (CTA or CTA pair), so the pre-pass is one short balanced wave.
+    const int units = use_pair ? std::max(1, h->num_sms / 2) : h->num_sms;
+    const int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (2 * units)));
     if (stride > 1) {
-      const int KLs = std::max(8, std::min(KL, (4 * KL + stride - 1) / stride));
+      // the KLs-th best of a 1/stride sample ranks about KLs*stride in the corpus: >= 4*KL and at least 10,
+      // so the chance that it lands inside the true top KL (which would starve the shortlist) is negligible
+      const int KLs = std::max(10, std::min(KL, (4 * KL + stride - 1) / stride));
       p.KL = KLs;
       p.tile_stride = stride;
       p.tile_count = (num_ctiles + stride - 1) / stride;
