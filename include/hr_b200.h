@@ -153,6 +153,19 @@ int hr_fuse(const float* dense_D, const int64_t* dense_I, const float* bm25_S,
             int metric, int mode, float w_vec, float w_bm25, float* out_S, int64_t* out_I,
             int device, void* stream);
 
+/* ---- row sharding: a rank's local candidates, then merge + fusion of all ranks' ------
+ * hr_candidates: dense top-kc (D,I) and BM25 top-kc (S,J) of THIS shard with global ids (id_base),
+ * all device pointers [nq,kc]; bm may be NULL (S=0, J=-1).  Returns after the results are complete.
+ * hr_merge_fuse_lists: n_lists candidate sets laid out list_stride_bytes apart (the per-rank blocks of
+ * one all-gather, read in place; list order = rank order = id order), merged per modality under
+ * (score best first, id asc) and fused to [nq, top_k].  Asynchronous on `stream`. */
+int hr_candidates(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
+                  const int32_t* q_terms, int64_t nq, int64_t n_terms, int kc, float* D, int64_t* I,
+                  float* S, int64_t* J, void* stream);
+int hr_merge_fuse_lists(hr_index* ix, const float* D, const int64_t* I, const float* S, const int64_t* J,
+                        int n_lists, int64_t list_stride_bytes, int64_t nq, int kc, int top_k, int mode,
+                        float w_vec, float w_bm25, float* out_S, int64_t* out_I, void* stream);
+
 /* ---- the whole query hot path on one device: dense + BM25 + fusion --------------------
  * retrieve(query_embeddings, query_tokens, top_k) of rag/query/retriever.py (path
  * advertised at README.md:90).  bm may be NULL (dense only).  Host or device io. */

@@ -63,6 +63,9 @@ SYMBOLS = {
     "hr_merge_topk": (C.c_int, [_p, _p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _p, _p, C.c_int, _p]),
     "hr_fuse": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                           C.c_float, _p, _p, C.c_int, _p]),
+    "hr_candidates": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int, _p, _p, _p, _p, _p]),
+    "hr_merge_fuse_lists": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, _p, _p, _p]),
     "hr_retrieve": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                               _p, _p, C.c_int, _p]),
 }

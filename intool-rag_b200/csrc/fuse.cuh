@@ -92,11 +92,15 @@ fuse_kernel(const float* __restrict__ dD, const int64_t* __restrict__ dI, const 
   }
 }
 
-// k-way merge of candidate lists: S,I [nq][n_cand] -> best k (largest or smallest first), id asc ties.
+// k-way merge of candidate lists -> best k (largest or smallest first), id asc ties.
+// Candidate e of query q is entry c = e % kc of list l = e / kc, stored at l * list_stride + q * kc + c
+// (one list with kc = n_cand: the plain [nq][n_cand] layout; several lists: the all-gathered per-rank
+// buffers, read in place).
 constexpr int kMergeTopkCap = 2048;
 __global__ void __launch_bounds__(256)
-merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, int n_cand, int k, int largest,
-                  float pad_score, float* __restrict__ oS, int64_t* __restrict__ oI) {
+merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, int n_cand, int kc, int64_t s_stride,
+                  int64_t i_stride, int k, int largest, float pad_score, float* __restrict__ oS,
+                  int64_t* __restrict__ oI) {
   __shared__ float ss[kMergeTopkCap];
   __shared__ int64_t si[kMergeTopkCap];
   __shared__ int s_valid;
@@ -104,8 +108,9 @@ merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, in
   if (threadIdx.x == 0) s_valid = 0;
   __syncthreads();
   for (int e = threadIdx.x; e < n_cand; e += blockDim.x) {
-    float s = S[(size_t)q * n_cand + e];
-    int64_t id = I[(size_t)q * n_cand + e];
+    const int l = e / kc, c = e - l * kc;
+    float s = S[(size_t)l * s_stride + (size_t)q * kc + c];
+    int64_t id = I[(size_t)l * i_stride + (size_t)q * kc + c];
     ss[e] = largest ? s : -s;
     si[e] = id;
     if (id >= 0) atomicAdd(&s_valid, 1);

@@ -1026,7 +1026,8 @@ extern "C" int hr_merge_topk(const float* S, const int64_t* I, int64_t nq, int n
   if (nq == 0) return HR_OK;
   if (!S || !I || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
   HR_DEVICE(device);
-  merge_topk_kernel<<<(unsigned)nq, 256, 0, (cudaStream_t)stream>>>(S, I, n_cand, k, largest, pad_score, out_S, out_I);
+  merge_topk_kernel<<<(unsigned)nq, 256, 0, (cudaStream_t)stream>>>(S, I, n_cand, n_cand, 0, 0, k, largest, pad_score,
+                                                                    out_S, out_I);
   HR_LAUNCHED();
   return HR_OK;
 }
@@ -1042,6 +1043,72 @@ extern "C" int hr_fuse(const float* dense_D, const int64_t* dense_I, const float
   HR_DEVICE(device);
   fuse_kernel<<<(unsigned)nq, 256, 0, (cudaStream_t)stream>>>(dense_D, dense_I, bm25_S, bm25_I, bm25_max, kc, top_k,
                                                              metric, mode, w_vec, w_bm25, out_S, out_I);
+  HR_LAUNCHED();
+  return HR_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// row-sharded retrieval: local candidates of one shard, and the merge + fusion of the gathered shards
+// -------------------------------------------------------------------------------------------------
+extern "C" int hr_candidates(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
+                             const int32_t* q_terms, int64_t nq, int64_t n_terms, int kc, float* D, int64_t* I,
+                             float* S, int64_t* J, void* stream) {
+  if (!ix) return set_err(HR_ERR_INVALID, "null index");
+  if (nq < 0 || kc <= 0 || kc > kBmMaxK) return set_err(HR_ERR_INVALID, "candidates: kc must be in [1, 128]");
+  if (nq == 0) return HR_OK;
+  if (!q || !D || !I || !S || !J) return set_err(HR_ERR_INVALID, "null argument");
+  if (bm && !q_indptr) return set_err(HR_ERR_INVALID, "null query tokens");
+  if (bm && bm->device != ix->device) return set_err(HR_ERR_INVALID, "index and bm25 live on different devices");
+  HR_DEVICE(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // BM25 first (asynchronous), then the dense search (which synchronises the stream)
+  if (bm) {
+    HR_TRY(bm25_search_dev(bm, q_indptr, q_terms, nq, n_terms, kc, S, J, st, nullptr));
+  } else {
+    fill_pad_kernel<<<(int)std::min<int64_t>((nq * kc + 255) / 256, 1024), 256, 0, st>>>(S, J, nq * kc, 0.f);
+    HR_LAUNCHED();
+  }
+  return index_search_dev(ix, q, nq, kc, D, I, st);
+}
+
+extern "C" int hr_merge_fuse_lists(hr_index* ix, const float* D, const int64_t* I, const float* S, const int64_t* J,
+                                   int n_lists, int64_t list_stride_bytes, int64_t nq, int kc, int top_k, int mode,
+                                   float w_vec, float w_bm25, float* out_S, int64_t* out_I, void* stream) {
+  if (!ix) return set_err(HR_ERR_INVALID, "null index");
+  if (nq < 0 || kc <= 0 || top_k <= 0 || n_lists <= 0) return set_err(HR_ERR_INVALID, "bad merge_fuse arguments");
+  if (kc > kFuseMaxKc) return set_err(HR_ERR_INVALID, "merge_fuse: candidate depth kc must be <= 256");
+  if ((int64_t)n_lists * kc > kMergeTopkCap) return set_err(HR_ERR_INVALID, "merge_fuse: more than 2048 candidates per query");
+  if (list_stride_bytes % 8 != 0) return set_err(HR_ERR_INVALID, "merge_fuse: list stride must be a multiple of 8 bytes");
+  if (mode != HR_FUSE_WEIGHTED && mode != HR_FUSE_RRF) return set_err(HR_ERR_INVALID, "unknown fusion mode");
+  if (nq == 0) return HR_OK;
+  if (!D || !I || !S || !J || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
+  HR_DEVICE(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* dD = D;
+  const int64_t* dI = I;
+  const float* bS = S;
+  const int64_t* bI = J;
+  if (n_lists > 1) {
+    RetrieveScratch& rs = ix->rs;
+    HR_TRY(rs.dD.ensure((size_t)nq * kc * 4));
+    HR_TRY(rs.dI.ensure((size_t)nq * kc * 8));
+    HR_TRY(rs.bS.ensure((size_t)nq * kc * 4));
+    HR_TRY(rs.bI.ensure((size_t)nq * kc * 8));
+    const int largest = ix->metric == HR_METRIC_INNER_PRODUCT;
+    merge_topk_kernel<<<(unsigned)nq, 256, 0, st>>>(D, I, n_lists * kc, kc, list_stride_bytes / 4, list_stride_bytes / 8,
+                                                    kc, largest, largest ? HR_NEG_INF : -HR_NEG_INF, rs.dD.as<float>(),
+                                                    rs.dI.as<int64_t>());
+    HR_LAUNCHED();
+    merge_topk_kernel<<<(unsigned)nq, 256, 0, st>>>(S, J, n_lists * kc, kc, list_stride_bytes / 4, list_stride_bytes / 8,
+                                                    kc, 1, 0.f, rs.bS.as<float>(), rs.bI.as<int64_t>());
+    HR_LAUNCHED();
+    dD = rs.dD.as<float>();
+    dI = rs.dI.as<int64_t>();
+    bS = rs.bS.as<float>();
+    bI = rs.bI.as<int64_t>();
+  }
+  fuse_kernel<<<(unsigned)nq, 256, 0, st>>>(dD, dI, bS, bI, nullptr, kc, top_k, ix->metric, mode, w_vec, w_bm25, out_S,
+                                            out_I);
   HR_LAUNCHED();
   return HR_OK;
 }

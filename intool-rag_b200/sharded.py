@@ -56,54 +56,72 @@ def gather_candidates(scores, ids, group=None):
 
 class ShardedRetriever:
     """Hybrid retrieval over row shards.  `index` / `bm25` hold THIS rank's shard with id_base set
-    to the shard's first global row and BM25 built with global statistics."""
+    to the shard's first global row and BM25 built with global statistics.
+
+    One step = hr_candidates (local BM25 + dense top-k_c into one packed buffer: D | S | I | J),
+    ONE all-gather of that buffer (24 * nq * k_c bytes per rank), hr_merge_fuse_lists reading the
+    gathered per-rank blocks in place (rank order == id order, comparator (score, id))."""
 
     def __init__(self, index, bm25=None, vector_weight: float = 0.7, bm25_weight: float = 0.3,
                  fusion: str = "weighted", group=None):
         self.index, self.bm25, self.group = index, bm25, group
         self.vector_weight, self.bm25_weight, self.fusion = vector_weight, bm25_weight, fusion
+        self._bufs = {}
+
+    @staticmethod
+    def _views(buf, n):
+        """(D float32[n], S float32[n], I int64[n], J int64[n]) views of one packed 24n-byte block."""
+        import torch
+        f = buf[:8 * n].view(torch.float32)
+        i = buf[8 * n:24 * n].view(torch.int64)
+        return f[:n], f[n:2 * n], i[:n], i[n:2 * n]
 
     def retrieve(self, query_embeddings, query_tokens=None, top_k: int = 10, k_c: int | None = None):
         """query_embeddings: torch CUDA float32 [nq, d] (replicated on every rank).  Returns torch CUDA
         (scores [nq, top_k], ids [nq, top_k]) — identical on every rank."""
         import torch
+        import torch.distributed as dist
         from .retriever import candidate_depth, _MODES
         kc = candidate_depth(top_k) if k_c is None else int(k_c)
-        q = query_embeddings
+        q = query_embeddings.to(torch.float32).contiguous()
         dev = q.device
         nq = q.shape[0]
-        D, I = self.index.search_device(q, kc)
-        largest = self.index.metric_type == _lib.METRIC_INNER_PRODUCT
+        if q.dim() != 2 or q.shape[1] != self.index.d:
+            raise AssertionError(f"retrieve: expected [nq, {self.index.d}] embeddings, got {tuple(q.shape)}")
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        n = nq * kc
+        key = (nq, kc, world)
+        if key not in self._bufs:
+            self._bufs = {key: (torch.empty(24 * n, dtype=torch.uint8, device=dev),
+                                torch.empty(world * 24 * n, dtype=torch.uint8, device=dev))}
+        local, gathered = self._bufs[key]
         use_bm = self.bm25 is not None and query_tokens is not None
+        qi = qt = None
         if use_bm:
             from .bm25 import query_csr
             ip, tm = query_csr(query_tokens)
             if not hasattr(ip, "is_cuda"):
                 ip = torch.from_numpy(np.ascontiguousarray(ip)).to(dev)
                 tm = torch.from_numpy(np.ascontiguousarray(tm)).to(dev)
-            S, J = self.bm25.search((ip, tm), kc)
-        else:
-            S = torch.zeros((nq, kc), dtype=torch.float32, device=dev)
-            J = torch.full((nq, kc), -1, dtype=torch.int64, device=dev)
-        Dg, Ig = gather_candidates(D, I, self.group)
-        Sg, Jg = gather_candidates(S, J, self.group)
+            qi, qt = ip.to(torch.int32).contiguous(), tm.to(torch.int32).contiguous()
+            if qi.shape[0] != nq + 1:
+                raise AssertionError("retrieve: query_tokens and query_embeddings disagree on nq")
         L = _lib.lib()
         st = _lib.current_stream_ptr(self.index.device)
-        if Dg.shape[1] != kc:
-            Dm = torch.empty((nq, kc), dtype=torch.float32, device=dev)
-            Im = torch.empty((nq, kc), dtype=torch.int64, device=dev)
-            pad = -3.4028234663852886e38 if largest else 3.4028234663852886e38
-            _lib.check(L.hr_merge_topk(Dg.data_ptr(), Ig.data_ptr(), nq, Dg.shape[1], kc, int(largest), pad,
-                                       Dm.data_ptr(), Im.data_ptr(), self.index.device, st))
-            Sm = torch.empty((nq, kc), dtype=torch.float32, device=dev)
-            Jm = torch.empty((nq, kc), dtype=torch.int64, device=dev)
-            _lib.check(L.hr_merge_topk(Sg.data_ptr(), Jg.data_ptr(), nq, Sg.shape[1], kc, 1, 0.0,
-                                       Sm.data_ptr(), Jm.data_ptr(), self.index.device, st))
+        D, S, I, J = self._views(local, n)
+        _lib.check(L.hr_candidates(self.index._h, self.bm25._h if use_bm else None, q.data_ptr(),
+                                   qi.data_ptr() if use_bm else None, qt.data_ptr() if use_bm else None, nq,
+                                   int(qt.numel()) if use_bm else 0, kc, D.data_ptr(), I.data_ptr(), S.data_ptr(),
+                                   J.data_ptr(), st))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local, group=self.group)
+            src = gathered
         else:
-            Dm, Im, Sm, Jm = Dg, Ig, Sg, Jg
+            src = local
+        D, S, I, J = self._views(src, n)
         oS = torch.empty((nq, top_k), dtype=torch.float32, device=dev)
         oI = torch.empty((nq, top_k), dtype=torch.int64, device=dev)
-        _lib.check(L.hr_fuse(Dm.data_ptr(), Im.data_ptr(), Sm.data_ptr(), Jm.data_ptr(), None, nq, kc, top_k,
-                             self.index.metric_type, _MODES[self.fusion], self.vector_weight, self.bm25_weight,
-                             oS.data_ptr(), oI.data_ptr(), self.index.device, st))
+        _lib.check(L.hr_merge_fuse_lists(self.index._h, D.data_ptr(), I.data_ptr(), S.data_ptr(), J.data_ptr(), world,
+                                         24 * n, nq, kc, top_k, _MODES[self.fusion], self.vector_weight,
+                                         self.bm25_weight, oS.data_ptr(), oI.data_ptr(), st))
         return oS, oI

@@ -174,7 +174,7 @@ def test_two_shards_on_one_gpu_equal_single_index(gpu):
     full_bm = pbm25.BM25Index.from_csr(indptr, pd, tf, dl, V)
     S, I = HybridRetriever(full_ix, full_bm).retrieve(q, qs, 10)
     df = np.diff(indptr)
-    outs = []
+    outs, blocks = [], []
     for rank in range(2):
         lo, hi = shard_bounds(n, 2, rank)
         ix = hf.IndexFlatIP(d)
@@ -189,6 +189,18 @@ def test_two_shards_on_one_gpu_equal_single_index(gpu):
         D, Id = ix.search(qd, 50)
         Sb, Ib = bm.search(pbm25.query_csr(qs), 50)
         outs.append((D, Id, torch.from_numpy(Sb).cuda(), torch.from_numpy(Ib).cuda()))
+        # the packed block hr_candidates writes on this "rank" (what the single all-gather carries)
+        nn = nq * 50
+        blk = torch.empty(24 * nn, dtype=torch.uint8, device="cuda")
+        Dv, Sv, Iv, Jv = ShardedRetriever._views(blk, nn)
+        qi_np, qt_np = pbm25.query_csr(qs)
+        qi_d, qt_d = torch.from_numpy(qi_np).cuda(), torch.from_numpy(qt_np).cuda()
+        _lib.check(_lib.lib().hr_candidates(ix._h, bm._h, qd.data_ptr(), qi_d.data_ptr(), qt_d.data_ptr(), nq,
+                                            int(qt_d.numel()), 50, Dv.data_ptr(), Iv.data_ptr(), Sv.data_ptr(),
+                                            Jv.data_ptr(), _lib.current_stream_ptr(0)))
+        assert torch.equal(Dv.view(nq, 50), D) and torch.equal(Iv.view(nq, 50), Id)
+        assert torch.equal(Jv.view(nq, 50), outs[-1][3]) and torch.equal(Sv.view(nq, 50), outs[-1][2])
+        blocks.append(blk)
     Dg = torch.cat([outs[0][0], outs[1][0]], 1).contiguous()
     Ig = torch.cat([outs[0][1], outs[1][1]], 1).contiguous()
     Sg = torch.cat([outs[0][2], outs[1][2]], 1).contiguous()
@@ -208,6 +220,15 @@ def test_two_shards_on_one_gpu_equal_single_index(gpu):
     # merged dense candidates equal the unsharded dense search exactly
     Df, If = full_ix.search(q, 50)
     assert np.array_equal(Im.cpu().numpy(), If) and np.array_equal(Dm.cpu().numpy(), Df)
+    # merge + fusion straight from the gathered per-rank blocks (the N>1 path): same answer
+    gathered = torch.cat(blocks)
+    nn = nq * 50
+    Dv, Sv, Iv, Jv = ShardedRetriever._views(gathered, nn)
+    gS, gI = torch.empty((nq, 10), device="cuda"), torch.empty((nq, 10), dtype=torch.int64, device="cuda")
+    _lib.check(L.hr_merge_fuse_lists(full_ix._h, Dv.data_ptr(), Iv.data_ptr(), Sv.data_ptr(), Jv.data_ptr(), 2, 24 * nn,
+                                     nq, 50, 10, 0, 0.7, 0.3, gS.data_ptr(), gI.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(gI, oI) and torch.equal(gS, oS)
     # single-rank ShardedRetriever (no process group) is the same call path the N>1 bench uses
     S1, I1 = ShardedRetriever(full_ix, full_bm).retrieve(torch.from_numpy(q).cuda(), qs, 10)
     assert np.array_equal(I1.cpu().numpy(), I)

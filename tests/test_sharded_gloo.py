@@ -55,6 +55,18 @@ def _worker(rank, world, port, out_dir):
     Dg, Ig = sharded.gather_candidates(torch.from_numpy(D), torch.from_numpy(I))
     Sg, Jg = sharded.gather_candidates(torch.from_numpy(S), torch.from_numpy(J))
     assert Dg.shape == (nq, world * kc)
+    # the packed single all-gather the GPU path uses (D | S | I | J per rank, 24 bytes per candidate):
+    # rank r's block must hold exactly rank r's four lists
+    nn = nq * kc
+    loc = torch.empty(24 * nn, dtype=torch.uint8)
+    for view, arr in zip(sharded.ShardedRetriever._views(loc, nn), (D, S, I, J)):
+        view.copy_(torch.from_numpy(np.ascontiguousarray(arr)).reshape(-1))
+    gathered = torch.empty(world * 24 * nn, dtype=torch.uint8)
+    dist.all_gather_into_tensor(gathered, loc)
+    for r in range(world):
+        Dr, Sr, Ir, Jr = sharded.ShardedRetriever._views(gathered[r * 24 * nn:(r + 1) * 24 * nn], nn)
+        assert torch.equal(Dr.view(nq, kc), Dg[:, r * kc:(r + 1) * kc]) and torch.equal(Ir.view(nq, kc), Ig[:, r * kc:(r + 1) * kc])
+        assert torch.equal(Sr.view(nq, kc), Sg[:, r * kc:(r + 1) * kc]) and torch.equal(Jr.view(nq, kc), Jg[:, r * kc:(r + 1) * kc])
     Dm, Im = fusion.merge_shards(Dg.numpy(), Ig.numpy(), kc, largest=True, pad_score=-flat.FLT_MAX)
     Sm, Jm = fusion.merge_shards(Sg.numpy(), Jg.numpy(), kc, largest=True, pad_score=0.0)
     fs, fi = fusion.fuse(Dm, Im, Sm, Jm, 10)
