@@ -334,14 +334,20 @@ def run_b200(args):
     note = ("kind::tf32 MMA runs at half the bf16 rate the peak was measured with (cuBLAS bf16, sustained)"
             if args.storage == "f32" else
             "kind::f16 (bf16 operands, fp32 accumulate in TMEM) over the bf16 rows; answers are exact fp32 after the re-score")
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture of this
+    # exact default workload (profiles/r1_scan_bm25_ncu_full.md); other workloads: not captured
+    traffic = None
+    if (world, args.rows, args.dim, args.nq, args.storage) == (1, 10_000_000, 1024, 1024, "f32+bf16"):
+        traffic = 20.798e9 + 0.083e9
     roofline = {"kernel": kname, "bound": bound, "achieved": achieved, "peak": peak, "unit": runit,
-                "frac": achieved / peak, "traffic": None, "peak_source": pk["src"],
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1_scan_bm25_ncu_full.md)",
+                "peak_source": pk["src"],
                 "kernel_ms": scan_ms, "share_of_step": scan_ms / ms_per_step,
                 "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": corpus_bytes,
                 "hbm_gbs_algorithmic": corpus_bytes / scan_s / 1e9,
                 "hbm_frac_algorithmic": corpus_bytes / scan_s / 1e9 / pk["hbm_gbs"],
                 "note": note,
-                "bm25": {"kernel": "bm25_score_kernel", "bound": "hbm", "postings": int(touched), "ms": bm_ms,
+                "bm25": {"kernel": "bm25_slice_kernel (+ plan kernels)", "bound": "hbm", "postings": int(touched), "ms": bm_ms,
                          "achieved": touched * 8 / (bm_ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": touched * 8 / (bm_ms / 1e3) / 1e9 / pk["hbm_gbs"]}}
     line = {"metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
