@@ -61,6 +61,7 @@ struct ScanParams {
   Cand* lists;         // [gridDim.x][nq][KL]
   int* cnts;           // [gridDim.x][nq]
   unsigned int* tau_g; // [nq] ordered-uint threshold, 0 = unset
+  float* pre_max;      // threshold pre-pass: [tile_count][nq] best score of each sampled tile (nullptr = main pass)
 };
 
 __device__ __noinline__ void cand_insert(Cand* list, int KL, float v, uint32_t row, float& tau_l, uint32_t& cnt,
@@ -92,6 +93,27 @@ __device__ __noinline__ void cand_insert(Cand* list, int KL, float v, uint32_t r
 
 // One (corpus tile, query tile) accumulator: thread = query q (TMEM lane), 256 columns = corpus rows.
 // Reads the accumulator in 32-column chunks and feeds scores above the query's threshold to its list.
+// Threshold pre-pass: no lists, only the best score of the tile for this query (31 FMNMX per 32 scores).
+template <int METRIC>
+__device__ __forceinline__ void scan_epilogue_max(ScanSmemTail* st, const ScanParams& p, uint32_t taddr, int q, int nb,
+                                                  int col_limit, int tile_slot) {
+  float best = HR_NEG_INF;
+#pragma unroll 1
+  for (int ch = 0; ch < kScanBN / 32; ++ch) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + ch * 32, r);
+    tmem_ld_wait();
+    const int cbase = ch * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = __uint_as_float(r[j]);
+      if (METRIC == 1) v -= st->half_norms[nb][cbase + j];
+      if (cbase + j < col_limit) best = fmaxf(best, v);
+    }
+  }
+  if (q < p.nq) p.pre_max[(size_t)tile_slot * p.nq + q] = best;
+}
+
 template <int METRIC>
 __device__ __forceinline__ void scan_epilogue_item(ScanSmemTail* st, const ScanParams& p, uint32_t taddr, int q, int nb,
                                                    int col_limit, uint32_t row0) {
@@ -273,8 +295,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int q = m * kScanBM + ew * 32 + lane;
         mbar_wait(&st->tmem_full[as], aphase);
         tc_fence_after();
-        scan_epilogue_item<METRIC>(st, p, tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16), q, nb, col_limit,
-                                   row0);
+        if (p.pre_max)
+          scan_epilogue_max<METRIC>(st, p, tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16), q, nb, col_limit, t);
+        else
+          scan_epilogue_item<METRIC>(st, p, tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16), q, nb, col_limit,
+                                     row0);
         tc_fence_before();
         mbar_arrive(&st->tmem_empty[as]);
       }
@@ -446,8 +471,11 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int q = m * 256 + (int)rank * 128 + ew * 32 + lane;
         mbar_wait(&st->tmem_full[as], aphase);
         tc_fence_after();
-        scan_epilogue_item<METRIC>(st, p, tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16), q, nb, col_limit,
-                                   row0);
+        if (p.pre_max)
+          scan_epilogue_max<METRIC>(st, p, tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16), q, nb, col_limit, t);
+        else
+          scan_epilogue_item<METRIC>(st, p, tmem_base + as * kScanBN + ((uint32_t)(ew * 32) << 16), q, nb, col_limit,
+                                     row0);
         tc_fence_before();
         mbar_arrive_leader(&st->tmem_empty[as]);
       }
@@ -475,11 +503,13 @@ __device__ __forceinline__ int merge_compact(const Cand* __restrict__ lists, con
                                              int* s_n) {
   if (threadIdx.x == 0) *s_n = 0;
   __syncthreads();
-  const int total = G * KL;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    int g = i / KL, j = i - g * KL;
-    if (j < cnts[(size_t)g * nq + q]) {
-      Cand c = lists[((size_t)g * nq + q) * KL + j];
+  // a warp per list, lanes over its entries: only the filled part of each list is read
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int g = warp; g < G; g += nwarp) {
+    const int cnt = min(cnts[(size_t)g * nq + q], KL);
+    const Cand* l = lists + ((size_t)g * nq + q) * KL;
+    for (int j = lane; j < cnt; j += 32) {
+      const Cand c = l[j];
       if (c.s >= tstar && f2ord(c.s) >= ord_min) {
         int slot = atomicAdd(s_n, 1);
         if (slot < kShortCap) buf[slot] = make_key(c.s, c.row);
@@ -568,6 +598,38 @@ scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
     // threshold pre-pass: the KL-th best score of the SAMPLE is a valid lower bound of the KL-th best
     // of the whole corpus (the sample rows are corpus rows) -> seed of tau_g for the main pass
     if (tau_seed) tau_seed[q] = (n >= KL) ? (uint32_t)(buf[KL - 1] >> 32) : o;
+  }
+}
+
+// ---- threshold seed from the pre-pass ---------------------------------------------------------------
+// pre_max [T][nq]: the best filter score of each of T sampled tiles (each the score of a distinct corpus
+// row).  The j-th largest of them is <= the j-th best score of the sample, whose rank in the corpus is about
+// j * stride: a valid, deliberately loose lower bound of the query's KL-th best.  One warp per query.
+__global__ void __launch_bounds__(256)
+scan_seed_kernel(const float* __restrict__ pre_max, int T, int nq, int j, unsigned int* __restrict__ tau_g) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  // value with exactly j-1 ... values above it under the total order (value desc, tile asc): rank by counting
+  float seed = HR_NEG_INF;
+  bool found = false;
+  for (int a = lane; a < ((T + 31) & ~31); a += 32) {
+    const float va = a < T ? pre_max[(size_t)a * nq + q] : HR_NEG_INF;
+    int rank = 0;
+    if (a < T)
+      for (int b = 0; b < T; ++b) {
+        const float vb = pre_max[(size_t)b * nq + q];
+        rank += (vb > va) || (vb == va && b < a);
+      }
+    if (a < T && rank == j - 1) {
+      seed = va;
+      found = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, found);
+  if (m) {
+    seed = __shfl_sync(0xffffffffu, seed, __ffs(m) - 1);
+    if (lane == 0 && seed > HR_NEG_INF) tau_g[q] = f2ord(seed);
   }
 }
 

@@ -148,7 +148,7 @@ struct hr_index {
   __nv_bfloat16* xs = nullptr;  // F32_SHADOW16 only: bf16 copy of the rows for the tensor-core filter, [capacity][ld]
   float* norms = nullptr;
   unsigned int* max_norm2 = nullptr;  // ordered-uint of max |x|^2
-  DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_n, tprime, flagged, counters;
+  DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_n, tprime, flagged, counters, pre_max;
   DevBuf ex_lists, ex_cnts, ex_tau, ex_sel, io_q, io_D, io_I, stage;
   int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -229,7 +229,7 @@ extern "C" int hr_index_destroy(hr_index* h) {
   if (h->max_norm2) cudaFree(h->max_norm2);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   DevBuf* bufs[] = {&h->qpad, &h->qh, &h->lists, &h->cnts, &h->tau_g, &h->short_rows, &h->short_n, &h->tprime,
-                    &h->flagged, &h->counters, &h->ex_lists, &h->ex_cnts, &h->ex_tau, &h->ex_sel, &h->io_q,
+                    &h->flagged, &h->counters, &h->pre_max, &h->ex_lists, &h->ex_cnts, &h->ex_tau, &h->ex_sel, &h->io_q,
                     &h->io_D, &h->io_I, &h->stage, &h->rs.q, &h->rs.qi, &h->rs.qt, &h->rs.dD, &h->rs.dI,
                     &h->rs.bS, &h->rs.bI, &h->rs.oS, &h->rs.oI};
   for (DevBuf* b : bufs) b->release();
@@ -560,6 +560,7 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     p.lists = h->lists.as<Cand>();
     p.cnts = h->cnts.as<int>();
     p.tau_g = h->tau_g.as<unsigned int>();
+    p.pre_max = nullptr;
     // batches of more than 128 queries run on CTA pairs (cta_group::2, 128-row corpus halves per CTA)
     const bool use_pair = nb > kScanBM && h->num_sms >= 2 && !getenv("HR_NO_PAIR");
     CUtensorMap tx2;
@@ -589,21 +590,20 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     const int units = use_pair ? std::max(1, h->num_sms / 2) : h->num_sms;
     const int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (2 * units)));
     if (stride > 1) {
-      // the KLs-th best of a 1/stride sample ranks about KLs*stride in the corpus: >= 4*KL and at least 10,
-      // so the chance that it lands inside the true top KL (which would starve the shortlist) is negligible
-      const int KLs = std::max(10, std::min(KL, (4 * KL + stride - 1) / stride));
-      p.KL = KLs;
+      // the j-th largest tile maximum ranks about j*stride in the corpus: >= 4*KL and at least 10, so the
+      // chance that it lands inside the true top KL (which would starve the shortlist) is negligible
       p.tile_stride = stride;
       p.tile_count = (num_ctiles + stride - 1) / stride;
+      const int jth = std::min(p.tile_count, std::max(10, (4 * KL + stride - 1) / stride));
+      HR_TRY(h->pre_max.ensure((size_t)p.tile_count * nb * 4));
+      p.pre_max = h->pre_max.as<float>();
       const int gs = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1)
                               : std::min(p.tile_count, h->num_sms);
       HR_TRY(run_scan(gs));
-      scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), gs,
-                                            nb, KLs, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
-                                            h->tprime.as<float>(), h->counters.as<int>() + 1,
-                                            h->tau_g.as<unsigned int>());
+      scan_seed_kernel<<<(nb + 7) / 8, 256, 0, st>>>(h->pre_max.as<float>(), p.tile_count, nb, jth,
+                                                     h->tau_g.as<unsigned int>());
       HR_LAUNCHED();
-      p.KL = KL;
+      p.pre_max = nullptr;
     }
     p.tile_stride = 1;
     p.tile_count = num_ctiles;
