@@ -119,7 +119,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_json_out, flush=True)
 
 
 def workload_config(args, n_gpus):
@@ -372,12 +372,17 @@ def run_b200(args):
             m = float(np.median(ms))
             log(f"[sweep] nq={nq:5d} scan {m:8.3f} ms  algorithmic HBM {corpus_bytes / m / 1e6:8.1f} GB/s "
                 f"({corpus_bytes / m / 1e6 / pk['hbm_gbs']:.3f} of peak)  {2.0 * nq * n_local * args.dim / m / 1e9:8.1f} TFLOP/s")
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) is
+    # sent to stderr instead; the JSON goes to a private duplicate of the original stdout
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

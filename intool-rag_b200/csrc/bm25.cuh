@@ -443,6 +443,56 @@ __device__ __forceinline__ void bs_warp_run(const int32_t* __restrict__ post_doc
     }
     if (nhot > kBsHotCap) {
       // cold thresholds: sweep the slice, extract and clear
+      if (tau == 0) {
+        // No threshold at all yet (first slice of a cold warp): appending every scored doc would cost a
+        // bitonic compaction per 64 docs.  Take each lane's best m = ceil(kc/32) scores first; the kc-th
+        // largest of those 32m scores (distinct docs of this slice) is a valid lower bound of the kc-th best.
+        float top[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = lane * 4; j < kBsSlice; j += 128) {
+          const float4 v = *reinterpret_cast<const float4*>(acc + j);
+          const float ve[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            float x = ve[e4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {   // insertion into the descending top-4
+              const float hi = fmaxf(top[t], x);
+              x = fminf(top[t], x);
+              top[t] = hi;
+            }
+          }
+        }
+        const int m = (kc + 31) >> 5;   // 1..4
+        float seed = 0.f;
+        bool found = false;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (t < m) {
+            int rank = 0;   // values above top[t] under (value desc, lane asc, slot asc)
+            for (int l = 0; l < 32; ++l) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float o = __shfl_sync(0xffffffffu, top[u], l);
+                if (u < m) rank += (o > top[t]) || (o == top[t] && (l < lane || (l == lane && u < t)));
+              }
+            }
+            if (rank == kc - 1) {
+              seed = top[t];
+              found = true;
+            }
+          }
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, found);
+        if (fm) seed = __shfl_sync(0xffffffffu, seed, __ffs(fm) - 1);
+        if (fm && seed > 0.f) {
+          tau = make_key(seed, 0xFFFFFFFFu) - 1;   // every doc scoring >= seed still passes `key > tau`
+          tau_f = seed;
+          if (lane == 0) {
+            atomicMax(s_tau, tau);
+            atomicMax(tau_gq, tau);
+          }
+        }
+      }
 #pragma unroll 2
       for (int j = lane * 4; j < kBsSlice; j += 128) {
         float4 v = *reinterpret_cast<float4*>(acc + j);
@@ -546,8 +596,8 @@ bm25_slice_kernel(const int32_t* __restrict__ post_doc, const float* __restrict_
   __syncthreads();
 
   int cbn = 0;                 // keys in this warp's buffer (warp-uniform)
-  unsigned long long tau = 0;  // this warp's threshold key: a lower bound of the query's kc-th best
-  float tau_f = 0.f;
+  unsigned long long tau = s_tau;   // this warp's threshold key: a lower bound of the query's kc-th best
+  float tau_f = tau ? key_score(tau) : 0.f;
   if (nt <= 32)
     bs_warp_run<false>(post_doc, post_imp, curq, nt, nsl, s_begin, s_end, T, acc, s_slots[w], s_hot[w], cb, cbn, cbcap,
                        kc, tau, tau_f, &s_tau, tau_gq, lane);
