@@ -586,15 +586,18 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     //      seeds tau_g: about KLs*stride (= 4*KL) corpus rows beat it, so in the main pass only a handful
     //      of scores per CTA pass the threshold and no per-CTA list ever fills.  Correctness never depends
     //      on the seed: the certificate in rescore_finalize compares against the final threshold. ----
-    // Sample size: two tiles per scheduling unit (CTA or CTA pair), so the pre-pass is one short balanced wave.
+    // Sample size: four tiles per scheduling unit (CTA or CTA pair), so the pre-pass is one short balanced wave.
     const int units = use_pair ? std::max(1, h->num_sms / 2) : h->num_sms;
-    const int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (2 * units)));
+    const int tpu = getenv("HR_PRE_TILES") ? atoi(getenv("HR_PRE_TILES")) : 4;   // sampled tiles per unit
+    const int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (tpu * units)));
     if (stride > 1) {
-      // the j-th largest tile maximum ranks about j*stride in the corpus: >= 4*KL and at least 10, so the
-      // chance that it lands inside the true top KL (which would starve the shortlist) is negligible
+      // the j-th largest tile maximum ranks about j*stride in the corpus: about 2*KL (a tighter seed means
+      // fewer list insertions in the main pass); if it lands inside the true top KL the shortlist is
+      // shorter and the certificate compares against the seed itself, which still sits far below rank k
       p.tile_stride = stride;
       p.tile_count = (num_ctiles + stride - 1) / stride;
-      const int jth = std::min(p.tile_count, std::max(10, (4 * KL + stride - 1) / stride));
+      const int rk = getenv("HR_PRE_RANK") ? atoi(getenv("HR_PRE_RANK")) : 2;   // target rank of the seed, in KL
+      const int jth = std::min(p.tile_count, std::max(rk >= 4 ? 10 : 8, (rk * KL + stride - 1) / stride));
       HR_TRY(h->pre_max.ensure((size_t)p.tile_count * nb * 4));
       p.pre_max = h->pre_max.as<float>();
       const int gs = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1)
@@ -926,7 +929,8 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     return set_err(HR_ERR_INVALID, "bm25: query batch too large for the cursor table (split the batch)");
   // spans per query: ~8 waves of CTAs over the machine (3 resident per SM), bounded by the merge capacity;
   // a CTA wants at least one slice per warp
-  int64_t S = (8 * 3 * (int64_t)h->num_sms + nq - 1) / nq;
+  const int waves = getenv("HR_BM25_WAVES") ? atoi(getenv("HR_BM25_WAVES")) : 8;
+  int64_t S = ((int64_t)waves * 3 * h->num_sms + nq - 1) / nq;
   S = std::max<int64_t>(1, std::min<int64_t>({S, (nsl + kBsWarps - 1) / kBsWarps, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
   const int spc = (int)((nsl + S - 1) / S);
   S = (nsl + spc - 1) / spc;
