@@ -126,6 +126,18 @@ int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, const int32_t
                    int idf_variant, int64_t n_docs_global, double avgdl_global,
                    const int64_t* df_global, int is_device, int device, void* stream,
                    hr_bm25** out);
+/* Ingest side: build the CSR on the device from flat token occurrences term_ids /
+ * doc_ids int32[n_tokens] (host or device; the reference tokenises with text.lower().split(),
+ * rag/agent/query_processor.py:26, and builds no sparse index: rag/ingest/ingestion_pipeline.py:79-94).
+ * doc_len is the number of occurrences per doc.  Same statistics arguments as hr_bm25_create. */
+int hr_bm25_create_from_tokens(const int32_t* term_ids, const int32_t* doc_ids, int64_t n_tokens,
+                               int64_t n_docs, int64_t vocab, float k1, float b, int idf_variant,
+                               int64_t n_docs_global, double avgdl_global, const int64_t* df_global,
+                               int is_device, int device, void* stream, hr_bm25** out);
+/* Persistence of the BM25 index (the sidecar next to the faiss file; the reference persists no sparse
+ * index): "HRBM25" v1 = header + indptr + idf + postings + folded impacts. */
+int hr_bm25_save(hr_bm25* h, const char* path);
+int hr_bm25_load(const char* path, int device, hr_bm25** out);
 int hr_bm25_destroy(hr_bm25* h);
 int64_t hr_bm25_ndocs(const hr_bm25* h);
 int64_t hr_bm25_vocab(const hr_bm25* h);

@@ -54,6 +54,10 @@ SYMBOLS = {
     "hr_index_load": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_p)]),
     "hr_bm25_create": (C.c_int, [_p, _p, _p, _p, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_int,
                                  C.c_int64, C.c_double, _p, C.c_int, C.c_int, _p, C.POINTER(_p)]),
+    "hr_bm25_create_from_tokens": (C.c_int, [_p, _p, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_int,
+                                             C.c_int64, C.c_double, _p, C.c_int, C.c_int, _p, C.POINTER(_p)]),
+    "hr_bm25_save": (C.c_int, [_p, C.c_char_p]),
+    "hr_bm25_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_p)]),
     "hr_bm25_destroy": (C.c_int, [_p]),
     "hr_bm25_ndocs": (C.c_int64, [_p]),
     "hr_bm25_vocab": (C.c_int64, [_p]),

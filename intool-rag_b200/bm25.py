@@ -140,17 +140,77 @@ class BM25Index:
         return cls(h.value, dev)
 
     @classmethod
+    def from_tokens(cls, term_ids, doc_ids, n_docs: int, vocab: int, k1: float | None = None,
+                    b: float | None = None, idf: str | None = None, n_docs_global: int = 0,
+                    avgdl_global: float = 0.0, df_global=None, device: int | None = None) -> "BM25Index":
+        """Flat token occurrences (term_ids[i] occurs in doc_ids[i]), numpy or torch CUDA int32: the CSR is
+        built on the GPU (sort + run-length encode), nothing is materialised on the host."""
+        _lib.require_gpu()
+        dev = default_device() if device is None else int(device)
+        k1 = config.BM25_K1 if k1 is None else k1
+        b = config.BM25_B if b is None else b
+        idf = idf or config.BM25_IDF
+        on_dev = _is_torch_cuda(term_ids)
+        keep = []
+        if on_dev:
+            import torch
+            t = term_ids.to(torch.int32).contiguous()
+            d = doc_ids.to(torch.int32).contiguous()
+            keep += [t, d]
+            tp, dp, n = t.data_ptr(), d.data_ptr(), int(t.numel())
+            dfg = None
+            if df_global is not None:
+                g = df_global.to(torch.int64).contiguous()
+                keep.append(g)
+                dfg = g.data_ptr()
+            st = _lib.current_stream_ptr(dev)
+        else:
+            t = np.ascontiguousarray(term_ids, dtype=np.int32)
+            d = np.ascontiguousarray(doc_ids, dtype=np.int32)
+            keep += [t, d]
+            tp, dp, n = t.ctypes.data, d.ctypes.data, int(t.size)
+            dfg = None
+            if df_global is not None:
+                g = np.ascontiguousarray(df_global, dtype=np.int64)
+                keep.append(g)
+                dfg = g.ctypes.data
+            st = None
+        if int(d.shape[0]) != n:
+            raise ValueError("term_ids and doc_ids must have the same length")
+        h = C.c_void_p()
+        _lib.check(_lib.lib().hr_bm25_create_from_tokens(tp, dp, n, int(n_docs), int(vocab), float(k1), float(b),
+                                                         _IDF[idf], int(n_docs_global), float(avgdl_global), dfg,
+                                                         int(on_dev), dev, st, C.byref(h)))
+        return cls(h.value, dev)
+
+    @classmethod
     def from_docs(cls, docs: Sequence[Sequence[int]], vocab: int, **kw) -> "BM25Index":
         """docs: list of token-id lists (one per chunk, row i of the dense index = doc i)."""
-        doc_len = np.array([len(d) for d in docs], dtype=np.int32)
+        doc_len = np.array([len(d) for d in docs], dtype=np.int64)
         if len(docs) and doc_len.sum():
-            t = np.concatenate([np.asarray(d, dtype=np.int64) for d in docs if len(d)])
-            dd = np.repeat(np.arange(len(docs), dtype=np.int64), doc_len)
+            t = np.concatenate([np.asarray(d, dtype=np.int32) for d in docs if len(d)])
+            dd = np.repeat(np.arange(len(docs), dtype=np.int32), doc_len)
         else:
-            t = np.zeros(0, np.int64)
-            dd = np.zeros(0, np.int64)
-        indptr, pd, tf = build_csr(t, dd, len(docs), vocab)
-        return cls.from_csr(indptr, pd, tf, doc_len, vocab, **kw)
+            t = np.zeros(0, np.int32)
+            dd = np.zeros(0, np.int32)
+        if t.size and (t.min() < 0 or t.max() >= vocab):
+            raise ValueError("token id outside [0, vocab)")
+        return cls.from_tokens(t, dd, len(docs), vocab, **kw)
+
+    # -- persistence -------------------------------------------------------------------------------
+    def save(self, path: str) -> None:
+        """Write the index (postings, folded impacts, idf) next to the faiss file: "HRBM25" v1."""
+        import os
+        _lib.check(_lib.lib().hr_bm25_save(self._h, os.fsencode(str(path))))
+
+    @classmethod
+    def load(cls, path: str, device: int | None = None) -> "BM25Index":
+        import os
+        _lib.require_gpu()
+        dev = default_device() if device is None else int(device)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().hr_bm25_load(os.fsencode(str(path)), dev, C.byref(h)))
+        return cls(h.value, dev)
 
     # -- attributes ------------------------------------------------------------------------------
     @property

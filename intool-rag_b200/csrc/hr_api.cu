@@ -18,6 +18,7 @@
 #include "dense_exact.cuh"
 #include "dense_scan_tc.cuh"
 #include "bm25.cuh"
+#include "bm25_build.cuh"
 #include "fuse.cuh"
 
 using namespace hr;
@@ -902,6 +903,202 @@ extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, co
   if (d_tf) cudaFree(d_tf);
   if (d_dl) cudaFree(d_dl);
   d_tf = d_dl = nullptr;
+  *out = h;
+  return HR_OK;
+}
+
+// ---- ingest: CSR build from token occurrences on the device ------------------------------------------
+extern "C" int hr_bm25_create_from_tokens(const int32_t* term_ids, const int32_t* doc_ids, int64_t n_tokens,
+                                          int64_t n_docs, int64_t vocab, float k1, float b, int idf_variant,
+                                          int64_t n_docs_global, double avgdl_global, const int64_t* df_global,
+                                          int is_device, int device, void* stream, hr_bm25** out) {
+  if (!out) return set_err(HR_ERR_INVALID, "null out");
+  *out = nullptr;
+  if (n_tokens < 0 || n_docs < 0 || vocab <= 0 || vocab > (int64_t)0x7FFFFFFFll)
+    return set_err(HR_ERR_INVALID, "bad BM25 build arguments");
+  if (n_tokens > 0 && (!term_ids || !doc_ids)) return set_err(HR_ERR_INVALID, "null token arrays");
+  if (n_docs >= (int64_t)0x7FFFFFF0ll) return set_err(HR_ERR_INVALID, "too many docs for one shard");
+  int ndev = 0;
+  HR_TRY(hr_device_count(&ndev));
+  if (ndev <= 0) return set_err(HR_ERR_CUDA, "no CUDA device (hr_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(HR_ERR_INVALID, "device ordinal out of range");
+  HR_DEVICE(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf d_t, d_d, keys_a, keys_b, counts, nruns, tmp, indptr, pdoc, ptf, dlen, bad;
+  DevBuf* all[] = {&d_t, &d_d, &keys_a, &keys_b, &counts, &nruns, &tmp, &indptr, &pdoc, &ptf, &dlen, &bad};
+  auto cleanup = [&]() { for (DevBuf* x : all) x->release(); };
+  auto fail = [&](int rc) { cleanup(); return rc; };
+  const size_t nt = (size_t)std::max<int64_t>(n_tokens, 1);
+  const size_t nd = (size_t)std::max<int64_t>(n_docs, 1);
+  int rc = HR_OK;
+  if ((rc = keys_a.ensure(nt * 8)) || (rc = keys_b.ensure(nt * 8)) || (rc = counts.ensure(nt * 4)) ||
+      (rc = nruns.ensure(8)) || (rc = indptr.ensure((size_t)(vocab + 1) * 8)) || (rc = dlen.ensure(nd * 4)) ||
+      (rc = bad.ensure(8)))
+    return fail(rc);
+  const int32_t* tp = term_ids;
+  const int32_t* dp = doc_ids;
+  if (!is_device && n_tokens > 0) {
+    if ((rc = d_t.ensure(nt * 4)) || (rc = d_d.ensure(nt * 4))) return fail(rc);
+    if (cudaMemcpyAsync(d_t.p, term_ids, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(d_d.p, doc_ids, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return fail(set_err(HR_ERR_CUDA, "copy of token arrays failed"));
+    tp = d_t.as<int32_t>();
+    dp = d_d.as<int32_t>();
+  }
+  if (cudaMemsetAsync(dlen.p, 0, nd * 4, st) != cudaSuccess || cudaMemsetAsync(bad.p, 0, 8, st) != cudaSuccess ||
+      cudaMemsetAsync(nruns.p, 0, 8, st) != cudaSuccess)
+    return fail(set_err(HR_ERR_CUDA, "memset failed in the BM25 build"));
+  int64_t nnz = 0;
+  if (n_tokens > 0) {
+    const int blocks = (int)std::min<int64_t>((n_tokens + 255) / 256, 148 * 16);
+    tokens_to_keys_kernel<<<blocks, 256, 0, st>>>(tp, dp, n_tokens, vocab, n_docs, keys_a.as<uint64_t>(),
+                                                  dlen.as<int32_t>(), bad.as<unsigned long long>());
+    g_launches.fetch_add(1);
+    unsigned long long n_bad = 0;
+    if (cudaMemcpyAsync(&n_bad, bad.p, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+      return fail(set_err(HR_ERR_CUDA, "BM25 build: key kernel failed"));
+    if (n_bad) return fail(set_err(HR_ERR_INVALID, "token id outside [0, vocab) or doc id outside [0, n_docs)"));
+    int vbits = 1;
+    while (((int64_t)1 << vbits) < vocab) ++vbits;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tb, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), (int64_t)n_tokens, 0,
+                                   32 + vbits, st);
+    size_t tb2 = 0;
+    cub::DeviceRunLengthEncode::Encode(nullptr, tb2, keys_b.as<uint64_t>(), keys_a.as<uint64_t>(), counts.as<int32_t>(),
+                                       nruns.as<int64_t>(), (int64_t)n_tokens, st);
+    if ((rc = tmp.ensure(std::max(tb, tb2) + 256))) return fail(rc);
+    if (cub::DeviceRadixSort::SortKeys(tmp.p, tb, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), (int64_t)n_tokens, 0,
+                                       32 + vbits, st) != cudaSuccess ||
+        cub::DeviceRunLengthEncode::Encode(tmp.p, tb2, keys_b.as<uint64_t>(), keys_a.as<uint64_t>(),
+                                           counts.as<int32_t>(), nruns.as<int64_t>(), (int64_t)n_tokens,
+                                           st) != cudaSuccess)
+      return fail(set_err(HR_ERR_CUDA, "BM25 build: sort / run-length encode failed"));
+    g_launches.fetch_add(2);
+    if (cudaMemcpyAsync(&nnz, nruns.p, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+      return fail(set_err(HR_ERR_CUDA, "BM25 build: run count copy failed"));
+  }
+  if ((rc = pdoc.ensure((size_t)std::max<int64_t>(nnz, 1) * 4)) || (rc = ptf.ensure((size_t)std::max<int64_t>(nnz, 1) * 4)))
+    return fail(rc);
+  if (nnz > 0) {
+    const int blocks = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 16);
+    unique_to_postings_kernel<<<blocks, 256, 0, st>>>(keys_a.as<uint64_t>(), counts.as<int32_t>(), nnz,
+                                                      pdoc.as<int32_t>(), ptf.as<int32_t>());
+    g_launches.fetch_add(1);
+  }
+  term_offsets_kernel<<<(unsigned)((vocab + 1 + 255) / 256), 256, 0, st>>>(keys_a.as<uint64_t>(), nnz, vocab,
+                                                                          indptr.as<int64_t>());
+  g_launches.fetch_add(1);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    return fail(set_err(HR_ERR_CUDA, "BM25 build: CSR kernels failed"));
+  keys_b.release();
+  counts.release();
+  tmp.release();
+  d_t.release();
+  d_d.release();
+  // the CSR now lives on the device: a host df_global goes there too before the device-side create
+  DevBuf dfg;
+  const int64_t* dfp = df_global;
+  if (df_global && !is_device) {
+    if ((rc = dfg.ensure((size_t)vocab * 8))) return fail(rc);
+    if (cudaMemcpyAsync(dfg.p, df_global, (size_t)vocab * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      dfg.release();
+      return fail(set_err(HR_ERR_CUDA, "copy of df_global failed"));
+    }
+    dfp = dfg.as<int64_t>();
+  }
+  rc = hr_bm25_create(indptr.as<int64_t>(), pdoc.as<int32_t>(), ptf.as<int32_t>(), dlen.as<int32_t>(), n_docs, vocab,
+                      k1, b, idf_variant, n_docs_global, avgdl_global, dfp, 1, device, stream, out);
+  dfg.release();
+  cleanup();
+  return rc;
+}
+
+// ---- persistence: the BM25 sidecar the reference never wrote ---------------------
+// "HRBM25\0\1" | int64 N, V, nnz, id_base | indptr int64[V+1] | idf fp32[V] | post_doc int32[nnz] | post_imp fp32[nnz]
+static const char kBm25Magic[8] = {'H', 'R', 'B', 'M', '2', '5', 0, 1};
+
+static bool dev_to_file(FILE* f, const void* dev, size_t bytes, std::vector<char>& buf) {
+  const size_t chunk = (size_t)64 << 20;
+  for (size_t o = 0; o < bytes; o += chunk) {
+    const size_t n = std::min(chunk, bytes - o);
+    buf.resize(n);
+    if (cudaMemcpy(buf.data(), (const char*)dev + o, n, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    if (fwrite(buf.data(), 1, n, f) != n) return false;
+  }
+  return true;
+}
+static bool file_to_dev(FILE* f, void* dev, size_t bytes, std::vector<char>& buf) {
+  const size_t chunk = (size_t)64 << 20;
+  for (size_t o = 0; o < bytes; o += chunk) {
+    const size_t n = std::min(chunk, bytes - o);
+    buf.resize(n);
+    if (fread(buf.data(), 1, n, f) != n) return false;
+    if (cudaMemcpy((char*)dev + o, buf.data(), n, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  }
+  return true;
+}
+
+extern "C" int hr_bm25_save(hr_bm25* h, const char* path) {
+  if (!h || !path) return set_err(HR_ERR_INVALID, "null argument");
+  HR_DEVICE(h->device);
+  FILE* f = fopen(path, "wb");
+  if (!f) return set_err(HR_ERR_IO, std::string("cannot open for writing: ") + path);
+  int64_t hdr[4] = {h->N, h->V, h->nnz, h->id_base};
+  std::vector<char> buf;
+  bool ok = fwrite(kBm25Magic, 1, 8, f) == 8 && fwrite(hdr, 8, 4, f) == 4 &&
+            dev_to_file(f, h->indptr, (size_t)(h->V + 1) * 8, buf) && dev_to_file(f, h->idf, (size_t)h->V * 4, buf) &&
+            dev_to_file(f, h->post_doc, (size_t)h->nnz * 4, buf) && dev_to_file(f, h->post_imp, (size_t)h->nnz * 4, buf);
+  if (fclose(f) != 0) ok = false;
+  if (!ok) return set_err(HR_ERR_IO, std::string("write failed: ") + path);
+  return HR_OK;
+}
+
+extern "C" int hr_bm25_load(const char* path, int device, hr_bm25** out) {
+  if (!path || !out) return set_err(HR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  HR_TRY(hr_device_count(&ndev));
+  if (ndev <= 0) return set_err(HR_ERR_CUDA, "no CUDA device (hr_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(HR_ERR_INVALID, "device ordinal out of range");
+  FILE* f = fopen(path, "rb");
+  if (!f) return set_err(HR_ERR_IO, std::string("cannot open BM25 index file: ") + path);
+  char magic[8];
+  int64_t hdr[4] = {0, 0, 0, 0};
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kBm25Magic, 8) != 0 || fread(hdr, 8, 4, f) != 4 || hdr[0] < 0 ||
+      hdr[1] <= 0 || hdr[2] < 0) {
+    fclose(f);
+    return set_err(HR_ERR_IO, std::string("not a BM25 index file (HRBM25 v1) or corrupt header: ") + path);
+  }
+  HR_DEVICE(device);
+  hr_bm25* h = new hr_bm25();
+  h->device = device;
+  h->N = hdr[0];
+  h->V = hdr[1];
+  h->nnz = hdr[2];
+  h->id_base = hdr[3];
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  const size_t nz = (size_t)std::max<int64_t>(h->nnz, 1);
+  std::vector<char> buf;
+  bool ok = cudaMalloc((void**)&h->indptr, (size_t)(h->V + 1) * 8) == cudaSuccess &&
+            cudaMalloc((void**)&h->idf, (size_t)h->V * 4) == cudaSuccess &&
+            cudaMalloc((void**)&h->post_doc, (nz + 4) * 4) == cudaSuccess &&
+            cudaMalloc((void**)&h->post_imp, (nz + 4) * 4) == cudaSuccess;
+  if (!ok) {
+    (void)cudaGetLastError();
+    fclose(f);
+    hr_bm25_destroy(h);
+    return set_err(HR_ERR_NOMEM, "cudaMalloc failed for the BM25 index");
+  }
+  ok = file_to_dev(f, h->indptr, (size_t)(h->V + 1) * 8, buf) && file_to_dev(f, h->idf, (size_t)h->V * 4, buf) &&
+       file_to_dev(f, h->post_doc, (size_t)h->nnz * 4, buf) && file_to_dev(f, h->post_imp, (size_t)h->nnz * 4, buf);
+  fclose(f);
+  if (!ok) {
+    hr_bm25_destroy(h);
+    return set_err(HR_ERR_IO, std::string("truncated BM25 index file: ") + path);
+  }
   *out = h;
   return HR_OK;
 }
