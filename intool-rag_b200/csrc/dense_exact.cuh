@@ -64,29 +64,44 @@ __device__ __forceinline__ void warp_exact_scores(const T* __restrict__ xrow, co
   for (int f = 0; f < F; ++f) out[f] = warp_sum_xor(acc[f]);
 }
 
+// What the tensor-core filter does to an operand: kind::tf32 ignores the low 13 mantissa bits (truncation),
+// the bf16 paths round to nearest even.  filter_kind: 0 = operand used as stored, 1 = tf32, 2 = bf16.
+__device__ __forceinline__ float filter_view(float v, int filter_kind) {
+  if (filter_kind == 1) return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  if (filter_kind == 2) return __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
+
 // ---- add path ---------------------------------------------------------------------------------
-// src fp32 [n, d] -> dst T [n, ld] (zero padded), plus |x|^2 per row and the running max norm.
+// src fp32 [n, d] -> dst T [n, ld] (zero padded), plus |x|^2 per row, the running max norm
+// (max_norm2_ord[0]) and the running max of |x - filter_view(x)|^2 (max_norm2_ord[1]): the certificate's
+// bound on what the filter can get wrong (dense_exact.cuh: rescore_finalize_kernel).
 template <typename T>
 __global__ void convert_pad_norm_kernel(const float* __restrict__ src, int64_t n, int d, T* __restrict__ dst,
-                                        int ld, float* __restrict__ norms, unsigned int* __restrict__ max_norm2_ord) {
+                                        int ld, float* __restrict__ norms, unsigned int* __restrict__ max_norm2_ord,
+                                        int filter_kind) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp; r < n; r += nwarps) {
     const float* s = src + r * (int64_t)d;
     T* o = dst + r * (int64_t)ld;
-    float acc = 0.f;
+    float acc = 0.f, res = 0.f;
     for (int c = lane; c < ld; c += 32) {
       float v = (c < d) ? s[c] : 0.f;
       T t = (T)v;
       o[c] = t;
       float back = (float)t;
       acc = fmaf(back, back, acc);
+      const float dv = back - filter_view(back, filter_kind);
+      res = fmaf(dv, dv, res);
     }
     acc = warp_sum_xor(acc);
+    res = warp_sum_xor(res);
     if (lane == 0) {
       norms[r] = acc;
       atomicMax(max_norm2_ord, f2ord(acc));
+      atomicMax(max_norm2_ord + 1, f2ord(res));
     }
   }
 }
@@ -318,11 +333,11 @@ template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
 rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict__ qpad,
                         const uint32_t* __restrict__ short_rows, const int* __restrict__ short_n,
-                        const float* __restrict__ tprime, int KL, int k, float c_rel,
+                        const float* __restrict__ tprime, int KL, int k, float c_acc, int filter_kind,
                         const unsigned int* __restrict__ max_norm2_ord, int64_t id_base, float* __restrict__ D,
                         int64_t* __restrict__ I, int* __restrict__ flagged, int* __restrict__ nflag) {
   extern __shared__ uint64_t skeys[];  // [KL]
-  __shared__ float s_qn2;
+  __shared__ float s_qn2, s_dq2, s_qt2;
   __shared__ float s_ek;
   __shared__ int s_have_k;
   const int q = blockIdx.x;
@@ -333,10 +348,22 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
   const float* qv = qpad + (int64_t)q * ld;
   if (threadIdx.x == 0) s_have_k = 0;
   if (warp == 0) {
-    float a = 0.f;
-    for (int c = lane; c < ld; c += 32) a = fmaf(qv[c], qv[c], a);
+    // |q|^2, |q - q~|^2 and |q~|^2 with q~ = the query as the filter saw it
+    float a = 0.f, dq = 0.f, qt = 0.f;
+    for (int c = lane; c < ld; c += 32) {
+      const float v = qv[c], f = filter_view(v, filter_kind);
+      a = fmaf(v, v, a);
+      dq = fmaf(v - f, v - f, dq);
+      qt = fmaf(f, f, qt);
+    }
     a = warp_sum_xor(a);
-    if (lane == 0) s_qn2 = a;
+    dq = warp_sum_xor(dq);
+    qt = warp_sum_xor(qt);
+    if (lane == 0) {
+      s_qn2 = a;
+      s_dq2 = dq;
+      s_qt2 = qt;
+    }
   }
   for (int i = warp; i < n; i += nwarp) {
     uint32_t row = short_rows[(int64_t)q * KL + i];
@@ -375,9 +402,13 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
     } else if (!s_have_k) {
       ok = false;  // rows were dropped but fewer than k survived: cannot certify
     } else {
-      const float xn = sqrtf(ord2f(*max_norm2_ord));
+      // |q.x - q~.x~| = |dq.x + q~.dx| <= |dq| max|x| + |q~| max|dx| (Cauchy-Schwarz; dq, dx are the operands'
+      // actual rounding residuals, measured, not their worst case), plus the fp32 accumulation of d terms
+      const float xn = sqrtf(ord2f(max_norm2_ord[0]));
+      const float dxn = sqrtf(fmaxf(ord2f(max_norm2_ord[1]), 0.f));
       const float qn = sqrtf(s_qn2);
-      float eps = c_rel * qn * xn + 1e-6f * (s_qn2 + xn * xn) + 1e-30f;
+      float eps = 1.0001f * (sqrtf(s_dq2) * xn + sqrtf(s_qt2) * dxn) + c_acc * qn * xn + 1e-6f * (s_qn2 + xn * xn) +
+                  1e-30f;
       // map the exact k-th best into the filter's score domain
       float shat = (METRIC == kMetricIP) ? s_ek : 0.5f * (s_qn2 + s_ek);  // s_ek = -dist for L2
       ok = shat > tp + eps;

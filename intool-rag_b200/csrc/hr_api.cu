@@ -148,7 +148,7 @@ struct hr_index {
   void* x = nullptr;           // exact rows: fp32 (F32, F32_SHADOW16) or bf16 (BF16), [capacity][ld]
   __nv_bfloat16* xs = nullptr;  // F32_SHADOW16 only: bf16 copy of the rows for the tensor-core filter, [capacity][ld]
   float* norms = nullptr;
-  unsigned int* max_norm2 = nullptr;  // ordered-uint of max |x|^2
+  unsigned int* max_norm2 = nullptr;  // ordered-uints: [0] max |x|^2, [1] max |x - filter's view of x|^2
   DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_n, tprime, flagged, counters, pre_max;
   DevBuf ex_lists, ex_cnts, ex_tau, ex_sel, io_q, io_D, io_I, stage;
   int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow
@@ -209,8 +209,8 @@ extern "C" int hr_index_create(int d, int metric, int storage_dtype, int device,
   const int kelems = storage_dtype == HR_STORAGE_F32 ? 32 : 64;
   h->ld = ((d + kelems - 1) / kelems) * kelems;
   h->num_sms = prop.multiProcessorCount;
-  if (cudaMalloc((void**)&h->max_norm2, sizeof(unsigned int)) != cudaSuccess ||
-      cudaMemset(h->max_norm2, 0, sizeof(unsigned int)) != cudaSuccess ||
+  if (cudaMalloc((void**)&h->max_norm2, 2 * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(h->max_norm2, 0, 2 * sizeof(unsigned int)) != cudaSuccess ||
       cudaMallocHost((void**)&h->h_counters, 4 * sizeof(int)) != cudaSuccess) {
     (void)cudaGetLastError();
     delete h;
@@ -304,7 +304,8 @@ extern "C" int hr_index_add(hr_index* h, const float* x, int64_t n, int is_devic
     const int blocks = (int)std::min<int64_t>((nr + 7) / 8, (int64_t)h->num_sms * 8);
     if (h->storage != HR_STORAGE_BF16) {
       convert_pad_norm_kernel<float><<<blocks, 256, 0, st>>>(src, nr, h->d, (float*)h->x + row0 * h->ld, h->ld,
-                                                            h->norms + row0, h->max_norm2);
+                                                            h->norms + row0, h->max_norm2,
+                                                            h->storage == HR_STORAGE_F32 ? 1 : 2);
       if (h->storage == HR_STORAGE_F32_SHADOW16) {
         HR_LAUNCHED();
         const int64_t tot = nr * (int64_t)h->ld;
@@ -313,7 +314,7 @@ extern "C" int hr_index_add(hr_index* h, const float* x, int64_t n, int is_devic
       }
     } else
       convert_pad_norm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
-          src, nr, h->d, (__nv_bfloat16*)h->x + row0 * h->ld, h->ld, h->norms + row0, h->max_norm2);
+          src, nr, h->d, (__nv_bfloat16*)h->x + row0 * h->ld, h->ld, h->norms + row0, h->max_norm2, 0);
     HR_LAUNCHED();
     if (!is_device) HR_CUDA(cudaStreamSynchronize(st));  // staging buffer is reused
   }
@@ -326,7 +327,7 @@ extern "C" int hr_index_reset(hr_index* h) {
   if (!h) return set_err(HR_ERR_INVALID, "null index");
   HR_DEVICE(h->device);
   h->ntotal = 0;
-  HR_CUDA(cudaMemset(h->max_norm2, 0, sizeof(unsigned int)));
+  HR_CUDA(cudaMemset(h->max_norm2, 0, 2 * sizeof(unsigned int)));
   return HR_OK;
 }
 extern "C" int64_t hr_index_ntotal(const hr_index* h) { return h ? h->ntotal : -1; }
@@ -471,17 +472,18 @@ static int launch_scan2(hr_index* h, const CUtensorMap& tq, const CUtensorMap& t
 }
 
 template <typename T>
-static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_rel, float* D, int64_t* I, cudaStream_t st) {
+static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_acc, float* D, int64_t* I, cudaStream_t st) {
+  const int fk = filter_is_bf16(h) ? 2 : 1;   // how the filter rounded the query
   const size_t smem = (size_t)KL * 8;
   if (h->metric == HR_METRIC_INNER_PRODUCT)
     rescore_finalize_kernel<T, kMetricIP><<<nb, 256, smem, st>>>(
         (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
-        h->tprime.as<float>(), KL, k, c_rel, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(),
+        h->tprime.as<float>(), KL, k, c_acc, fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(),
         h->counters.as<int>());
   else
     rescore_finalize_kernel<T, kMetricL2><<<nb, 256, smem, st>>>(
         (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
-        h->tprime.as<float>(), KL, k, c_rel, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(),
+        h->tprime.as<float>(), KL, k, c_acc, fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(),
         h->counters.as<int>());
   HR_LAUNCHED();
   return HR_OK;
@@ -620,12 +622,11 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
                                           nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
                                           h->tprime.as<float>(), h->counters.as<int>() + 1, nullptr);
     HR_LAUNCHED();
-    // worst-case relative error of the filter score: both operands lose <= 2^-10 (tf32 truncation) or the
-    // query loses <= 2^-9 (bf16 rounding; bf16 rows are exact), plus fp32 accumulation over d terms
-    // (shadow: the stored row is rounded to bf16 as well, 2^-9 on each operand)
-    const float c_rel = (h->storage == HR_STORAGE_F32_SHADOW16 ? 3.92e-3f : 1.96e-3f) + 2.4e-7f * (float)h->ld;
-    if (h->elem == 4) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_rel, Db, Ib, st));
-    else HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_rel, Db, Ib, st));
+    // filter error bound = measured rounding residuals of both operands (rescore_finalize_kernel) + this
+    // relative allowance for the fp32 accumulation over ld terms
+    const float c_acc = 2.4e-7f * (float)h->ld;
+    if (h->elem == 4) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_acc, Db, Ib, st));
+    else HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_acc, Db, Ib, st));
     HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 8, cudaMemcpyDeviceToHost, st));
     HR_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
