@@ -54,6 +54,33 @@ static int set_err(int code, const std::string& msg) {
     HR_CUDA(cudaGetLastError());      \
   } while (0)
 
+// Tuning knobs, read once from the environment (defaults are the measured best on B200).
+struct Tuning {
+  int q_rows = 128;     // HR_QROWS: query rows materialised for the TMA box of small batches
+  int pre_tiles = 4;    // HR_PRE_TILES: corpus tiles per CTA (pair) sampled by the threshold pre-pass
+  int pre_rank = 2;     // HR_PRE_RANK: target corpus rank of the seeded threshold, in units of KL
+  int bm25_waves = 8;   // HR_BM25_WAVES: BM25 CTAs per resident slot
+  bool no_pair = false; // HR_NO_PAIR: never use the cta_group::2 scan kernel
+};
+static const Tuning& tuning() {
+  static const Tuning t = [] {
+    Tuning x;
+    auto geti = [](const char* name, int dflt, int lo, int hi) {
+      const char* v = getenv(name);
+      if (!v || !*v) return dflt;
+      const int i = atoi(v);
+      return i < lo ? lo : (i > hi ? hi : i);
+    };
+    x.q_rows = geti("HR_QROWS", x.q_rows, 1, 128);
+    x.pre_tiles = geti("HR_PRE_TILES", x.pre_tiles, 1, 64);
+    x.pre_rank = geti("HR_PRE_RANK", x.pre_rank, 1, 16);
+    x.bm25_waves = geti("HR_BM25_WAVES", x.bm25_waves, 1, 64);
+    x.no_pair = getenv("HR_NO_PAIR") != nullptr;
+    return x;
+  }();
+  return t;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
@@ -520,7 +547,7 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     int64_t* Ib = I_dev + q0 * k;
     // query rows materialised for the TMA (zero rows beyond nb): a full 128-row box, so that the SMs'
     // re-reads of a small batch spread over 128 rows instead of hammering a few L2 lines
-    const int nbp = std::max(nb, getenv("HR_QROWS") ? atoi(getenv("HR_QROWS")) : 128);
+    const int nbp = std::max(nb, tuning().q_rows);
     HR_TRY(h->qpad.ensure((size_t)nbp * h->ld * 4));
     if (filter_is_bf16(h)) HR_TRY(h->qh.ensure((size_t)nbp * h->ld * 2));
     {
@@ -565,7 +592,7 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     p.tau_g = h->tau_g.as<unsigned int>();
     p.pre_max = nullptr;
     // batches of more than 128 queries run on CTA pairs (cta_group::2, 128-row corpus halves per CTA)
-    const bool use_pair = nb > kScanBM && h->num_sms >= 2 && !getenv("HR_NO_PAIR");
+    const bool use_pair = nb > kScanBM && h->num_sms >= 2 && !tuning().no_pair;
     CUtensorMap tx2;
     if (use_pair) HR_TRY(make_tmap(&tx2, filter_rows(h), h->ntotal, h->ld, filter_elem(h), 128));
     auto run_scan = [&](int g) -> int {
@@ -591,7 +618,7 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     //      on the seed: the certificate in rescore_finalize compares against the final threshold. ----
     // Sample size: four tiles per scheduling unit (CTA or CTA pair), so the pre-pass is one short balanced wave.
     const int units = use_pair ? std::max(1, h->num_sms / 2) : h->num_sms;
-    const int tpu = getenv("HR_PRE_TILES") ? atoi(getenv("HR_PRE_TILES")) : 4;   // sampled tiles per unit
+    const int tpu = tuning().pre_tiles;   // sampled tiles per unit
     const int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (tpu * units)));
     if (stride > 1) {
       // the j-th largest tile maximum ranks about j*stride in the corpus: about 2*KL (a tighter seed means
@@ -599,7 +626,7 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
       // shorter and the certificate compares against the seed itself, which still sits far below rank k
       p.tile_stride = stride;
       p.tile_count = (num_ctiles + stride - 1) / stride;
-      const int rk = getenv("HR_PRE_RANK") ? atoi(getenv("HR_PRE_RANK")) : 2;   // target rank of the seed, in KL
+      const int rk = tuning().pre_rank;   // target rank of the seed, in KL
       const int jth = std::min(p.tile_count, std::max(rk >= 4 ? 10 : 8, (rk * KL + stride - 1) / stride));
       HR_TRY(h->pre_max.ensure((size_t)p.tile_count * nb * 4));
       p.pre_max = h->pre_max.as<float>();
@@ -1127,7 +1154,7 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     return set_err(HR_ERR_INVALID, "bm25: query batch too large for the cursor table (split the batch)");
   // spans per query: ~8 waves of CTAs over the machine (3 resident per SM), bounded by the merge capacity;
   // a CTA wants at least one slice per warp
-  const int waves = getenv("HR_BM25_WAVES") ? atoi(getenv("HR_BM25_WAVES")) : 8;
+  const int waves = tuning().bm25_waves;
   int64_t S = ((int64_t)waves * 3 * h->num_sms + nq - 1) / nq;
   S = std::max<int64_t>(1, std::min<int64_t>({S, (nsl + kBsWarps - 1) / kBsWarps, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
   const int spc = (int)((nsl + S - 1) / S);
