@@ -12,12 +12,12 @@
 //   bm25_plan_cursors_kernel per (query, term, slice boundary): lower_bound of the boundary's first
 //                            doc id in the term's posting list (two levels: every 16th boundary by a
 //                            search over the whole list, the others inside the bracketing pair).
-//                            The document axis is cut into slices of kBsSlice docs; with the cursor
+//                            The document axis is cut into slices of 3072 (2688) docs; with the cursor
 //                            table every (query, slice) is an independent, exactly-known set of
 //                            posting ranges.
 //   bm25_slice_kernel        A WARP owns a run of consecutive slices of one query and works alone:
 //                            no block barrier, no atomics on the accumulators.  The slice's
-//                            accumulators (kBsSlice fp32) live in the warp's shared memory.  The
+//                            accumulators (one fp32 per doc) live in the warp's shared memory.  The
 //                            posting ranges of the slice are cut into slots (<= 32 postings: one per
 //                            lane; otherwise 128 postings, four per lane with 16-byte loads); the
 //                            warp loads kBsBatch slots at once (all loads in flight before the first
@@ -39,14 +39,22 @@ constexpr int kBmMaxTerms = 64;   // raw terms per query
 constexpr int kBmMaxK = 128;      // candidate depth the kernel supports
 constexpr int kBsThreads = 256;
 constexpr int kBsWarps = kBsThreads / 32;
-constexpr int kBsSlice = 15 * 128;   // docs per warp slice (7.5 KB of accumulators)
+// Docs per warp slice.  Two CTAs (16 warps) per SM with the largest slice that fits measured best: fewer,
+// fuller slots beat more resident warps (3 x 8 warps x 1920 docs: 9.9 ms; 2 x 8 x 3072: 9.3 ms at C1).
+// The slice shrinks when the candidate buffers are large (k_c > 64) so that two CTAs still fit.
+constexpr int kBsSliceLarge = 24 * 128;   // k_c <= 64: 96 KB of accumulators + 8 KB of key buffers per CTA
+constexpr int kBsSliceSmall = 21 * 128;   // k_c <= 128: 84 KB + 16 KB
+constexpr int kBsCtasPerSm = 2;
+__host__ __device__ constexpr int bs_slice_docs(int kcp) { return kcp <= 64 ? kBsSliceLarge : kBsSliceSmall; }
 constexpr int kBsCoarse = 16;        // slice boundaries per coarse boundary in the cursor plan
 constexpr int kBsSlotCap = 32;       // slot descriptors per round (512 B per warp)
 constexpr int kBsSlotLen = 128;      // postings of a wide slot
-constexpr int kBsBatch = 4;          // slots a warp keeps in flight
+constexpr int kBsBatch = 5;          // slots a warp keeps in flight
 constexpr int kBsHotCap = 64;        // docs that may reach the threshold in one slice before the full sweep takes over
 // dynamic shared memory: accumulators | warp key buffers (2*kcp keys each)
-__host__ __device__ constexpr int bs_smem_bytes(int kcp) { return kBsWarps * kBsSlice * 4 + kBsWarps * 2 * kcp * 8; }
+__host__ __device__ constexpr int bs_smem_bytes(int kcp) {
+  return kBsWarps * bs_slice_docs(kcp) * 4 + kBsWarps * 2 * kcp * 8;
+}
 
 __global__ void bm25_impact_kernel(const int32_t* __restrict__ post_doc, const int32_t* __restrict__ post_tf,
                                    const int32_t* __restrict__ doc_len, int64_t nnz, double k1, double b,
@@ -316,7 +324,7 @@ __device__ __forceinline__ void bs_append(bool take, unsigned long long key, uin
 // from the thresholds earlier spans published in tau_g.  CTA (q, g) covers slices [g*spc, (g+1)*spc), its
 // warp w the sub-run [w*spw, (w+1)*spw) of that.  out_keys [nq][S][kc], out_n [nq][S].
 // kcp = power of two >= max(kc, 32); a warp's key buffer holds 2*kcp keys.
-template <bool TWO_HALVES>
+template <bool TWO_HALVES, int kBsSlice>
 __device__ __forceinline__ void bs_warp_run(const int32_t* __restrict__ post_doc, const float* __restrict__ post_imp,
                                             const uint32_t* __restrict__ curq, int nt, int64_t nsl, int64_t s_begin,
                                             int64_t s_end, BsTerms& T, float* acc, BsSlot* slots, uint16_t* hotl,
@@ -541,7 +549,8 @@ __device__ __forceinline__ void bs_warp_run(const int32_t* __restrict__ post_doc
   }
 }
 
-__global__ void __launch_bounds__(kBsThreads, 3)
+template <int kBsSlice>
+__global__ void __launch_bounds__(kBsThreads, kBsCtasPerSm)
 bm25_slice_kernel(const int32_t* __restrict__ post_doc, const float* __restrict__ post_imp,
                   const int32_t* __restrict__ q_indptr, const int* __restrict__ plan_nt,
                   const int64_t* __restrict__ plan_start, const float* __restrict__ plan_wgt,
@@ -599,10 +608,10 @@ bm25_slice_kernel(const int32_t* __restrict__ post_doc, const float* __restrict_
   unsigned long long tau = s_tau;   // this warp's threshold key: a lower bound of the query's kc-th best
   float tau_f = tau ? key_score(tau) : 0.f;
   if (nt <= 32)
-    bs_warp_run<false>(post_doc, post_imp, curq, nt, nsl, s_begin, s_end, T, acc, s_slots[w], s_hot[w], cb, cbn, cbcap,
+    bs_warp_run<false, kBsSlice>(post_doc, post_imp, curq, nt, nsl, s_begin, s_end, T, acc, s_slots[w], s_hot[w], cb, cbn, cbcap,
                        kc, tau, tau_f, &s_tau, tau_gq, lane);
   else
-    bs_warp_run<true>(post_doc, post_imp, curq, nt, nsl, s_begin, s_end, T, acc, s_slots[w], s_hot[w], cb, cbn, cbcap,
+    bs_warp_run<true, kBsSlice>(post_doc, post_imp, curq, nt, nsl, s_begin, s_end, T, acc, s_slots[w], s_hot[w], cb, cbn, cbcap,
                       kc, tau, tau_f, &s_tau, tau_gq, lane);
   // ---- warp list -> sorted top-kc ----
   for (int i = cbn + lane; i < cbcap; i += 32) cb[i] = 0;

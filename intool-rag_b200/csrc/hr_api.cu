@@ -1146,16 +1146,17 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   int kcp = 32;
   while (kcp < k) kcp <<= 1;
   const int smem = bs_smem_bytes(kcp);
-  const int64_t nsl = std::max<int64_t>(1, (h->N + kBsSlice - 1) / kBsSlice);   // slices; nsl + 1 boundaries
+  const int slice_docs = bs_slice_docs(kcp);
+  const int64_t nsl = std::max<int64_t>(1, (h->N + slice_docs - 1) / slice_docs);   // slices; nsl + 1 boundaries
   const int64_t nbc = (nsl + kBsCoarse - 1) / kBsCoarse + 1;                    // coarse boundaries
   const size_t nterm_slots = (size_t)std::max<int64_t>(n_terms, 1);
   const size_t cur_bytes = nterm_slots * (size_t)(nsl + 1) * 4;
   if (cur_bytes > ((size_t)16 << 30))
     return set_err(HR_ERR_INVALID, "bm25: query batch too large for the cursor table (split the batch)");
-  // spans per query: ~8 waves of CTAs over the machine (3 resident per SM), bounded by the merge capacity;
+  // spans per query: ~8 waves of CTAs over the machine (kBsCtasPerSm resident per SM), bounded by the merge capacity;
   // a CTA wants at least one slice per warp
   const int waves = tuning().bm25_waves;
-  int64_t S = ((int64_t)waves * 3 * h->num_sms + nq - 1) / nq;
+  int64_t S = ((int64_t)waves * kBsCtasPerSm * h->num_sms + nq - 1) / nq;
   S = std::max<int64_t>(1, std::min<int64_t>({S, (nsl + kBsWarps - 1) / kBsWarps, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
   const int spc = (int)((nsl + S - 1) / S);
   S = (nsl + spc - 1) / spc;
@@ -1179,25 +1180,29 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     dim3 gridc((unsigned)nq, (unsigned)((nbc + 255) / 256));
     bm25_plan_cursors_kernel<<<gridc, 256, 0, st>>>(h->post_doc, qi_dev, h->plan_nt.as<int>(),
                                                     h->plan_start.as<int64_t>(), h->plan_len.as<uint32_t>(), nbc,
-                                                    (int64_t)kBsSlice * kBsCoarse, nullptr, 0, 1,
+                                                    (int64_t)slice_docs * kBsCoarse, nullptr, 0, 1,
                                                     h->plan_coarse.as<uint32_t>());
     HR_LAUNCHED();
     dim3 grid((unsigned)nq, (unsigned)((nsl + 1 + 255) / 256));
     bm25_plan_cursors_kernel<<<grid, 256, 0, st>>>(h->post_doc, qi_dev, h->plan_nt.as<int>(),
                                                    h->plan_start.as<int64_t>(), h->plan_len.as<uint32_t>(), nsl + 1,
-                                                   (int64_t)kBsSlice, h->plan_coarse.as<uint32_t>(), nbc, kBsCoarse,
+                                                   (int64_t)slice_docs, h->plan_coarse.as<uint32_t>(), nbc, kBsCoarse,
                                                    h->plan_cur.as<uint32_t>());
     HR_LAUNCHED();
   }
-  HR_CUDA(cudaFuncSetAttribute(bm25_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   {
     dim3 grid((unsigned)nq, (unsigned)S);
-    bm25_slice_kernel<<<grid, kBsThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
-                                                      h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
-                                                      h->plan_cur.as<uint32_t>(), nsl, spc, (int)S, k, kcp,
-                                                      h->keys.as<uint64_t>(), h->ns.as<int>(),
-                                                      h->tau.as<unsigned long long>());
-    HR_LAUNCHED();
+    auto launch = [&](auto kern) -> int {
+      HR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      kern<<<grid, kBsThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
+                                           h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
+                                           h->plan_cur.as<uint32_t>(), nsl, spc, (int)S, k, kcp, h->keys.as<uint64_t>(),
+                                           h->ns.as<int>(), h->tau.as<unsigned long long>());
+      HR_LAUNCHED();
+      return HR_OK;
+    };
+    if (slice_docs == kBsSliceLarge) HR_TRY(launch(bm25_slice_kernel<kBsSliceLarge>));
+    else HR_TRY(launch(bm25_slice_kernel<kBsSliceSmall>));
   }
   bm25_merge_kernel<<<(unsigned)nq, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), (int)S, k, k, h->id_base,
                                                   S_dev, I_dev);
