@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--storage", default=os.getenv("HR_BENCH_STORAGE", "f32+bf16"), choices=["f32", "f32+bf16", "bf16"],
                     help="f32: fp32 rows, TF32 filter; f32+bf16: fp32 rows + bf16 shadow for the filter (same answers); "
                          "bf16: bf16 rows")
+    ap.add_argument("--index-metric", default="ip", choices=["ip", "l2"],
+                    help="ip: IndexFlatIP (BASELINE.json); l2: IndexFlatL2, what the reference builds "
+                         "(rag/storage/faiss_index.py:123); same ranking on unit-norm rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also print an nq sweep of the dense scan (stderr)")
     return ap.parse_args()
@@ -82,7 +85,7 @@ def cpu_reference(args, steps, warmup):
     q = synth.dense_queries_np(x, args.nq)
     t, dd, dl = synth.sparse_corpus_np(n, args.vocab)
     qs = synth.sparse_queries_np(args.nq, args.vocab)
-    ix = flat.IndexFlatIP(args.dim)
+    ix = flat.IndexFlatIP(args.dim) if args.index_metric == "ip" else flat.IndexFlatL2(args.dim)
     ix.add(x)
     corpus = obm25.BM25Corpus.from_token_matrix(t, dd, dl, args.vocab)
     times = []
@@ -123,7 +126,7 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus):
-    return {"workload": f"BASELINE configs[1]: {args.rows}x{args.dim} fp32 flat index (IndexFlatIP semantics, storage {args.storage}) + BM25 over "
+    return {"workload": f"BASELINE configs[1]: {args.rows}x{args.dim} fp32 flat index (IndexFlat{args.index_metric.upper()} semantics, storage {args.storage}) + BM25 over "
                         f"{args.rows} chunks ({args.vocab}-term Zipf vocabulary), batch {args.nq} queries, hybrid top-{args.topk}, "
                         "weighted fusion 0.7/0.3, candidate depth 50",
             "rows": args.rows, "dim": args.dim, "nq": args.nq, "top_k": args.topk, "vocab": args.vocab, "storage": args.storage,
@@ -208,7 +211,7 @@ def run_b200(args):
     t0 = time.time()
     lo, hi = shard_bounds(args.rows, world, rank)
     n_local = hi - lo
-    ix = hf.IndexFlatIP(args.dim, device=local, storage=args.storage)
+    ix = (hf.IndexFlatIP if args.index_metric == "ip" else hf.IndexFlatL2)(args.dim, device=local, storage=args.storage)
     ix.set_id_base(lo)
     planted = synth.dense_corpus_into(ix, n_local, args.dim, dev, seed=synth.DENSE_SEED + rank, keep_rows=4096)
     if world > 1:
@@ -330,7 +333,7 @@ def run_b200(args):
         achieved, peak, runit = flops / scan_s / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
     else:
         achieved, peak, runit = corpus_bytes / scan_s / 1e9, pk["hbm_gbs"], "GB/s"
-    kname = ("scan_tc2_kernel" if args.nq > 128 else "scan_tc_kernel") + ("<tf32,ip>" if args.storage == "f32" else "<bf16,ip>")
+    kname = ("scan_tc2_kernel" if args.nq > 128 else "scan_tc_kernel") + (f"<tf32,{args.index_metric}>" if args.storage == "f32" else f"<bf16,{args.index_metric}>")
     note = ("kind::tf32 MMA runs at half the bf16 rate the peak was measured with (cuBLAS bf16, sustained)"
             if args.storage == "f32" else
             "kind::f16 (bf16 operands, fp32 accumulate in TMEM) over the bf16 rows; answers are exact fp32 after the re-score")
