@@ -5,6 +5,11 @@ Same function names, arguments and error behaviour as /root/reference/rag/storag
 search_faiss_by_vector :137-199, initialize_storage :202-228) so the service code calls it
 unchanged.  Written against this package's :mod:`.faiss`; nothing is copied from the reference.
 
+On top of the mirror, the hybrid service path the reference advertises (README.md:54-58) but never
+shipped: `build_bm25_sidecar` (ingest: chunk texts -> BM25 index file + vocabulary next to the faiss
+file) and `search_hybrid_by_vector` (query vector + query text -> fused hits, same dict shape as
+`search_faiss_by_vector`).
+
 Deliberate, documented deviations:
   * padded hits (id -1, when limit > ntotal) are dropped instead of silently mapping to the LAST
     chunk through Python's negative indexing (faiss_index.py:180-181);
@@ -27,6 +32,7 @@ from .config import config
 logger = logging.getLogger("intool_rag_b200.storage")
 
 _INDEX_CACHE: Dict[Tuple[str, float], "faiss.Index"] = {}
+_BM25_CACHE: Dict[Tuple[str, float], tuple] = {}
 _CHUNK_CACHE: Dict[Tuple[str, float], List[dict]] = {}
 
 
@@ -169,3 +175,92 @@ async def initialize_storage() -> None:
         except Exception as e:
             logger.error("Failed to pre-load index %s: %s", path, e)
     logger.info("Initialized storage: loaded %d indices into HBM", count)
+
+
+# ---------------------------------------------------------------------------------------------------
+# hybrid service path (BM25 sidecar + fused search)
+# ---------------------------------------------------------------------------------------------------
+def _sidecar_paths(storage_dir: str, doc_id: str) -> Tuple[str, str]:
+    return (os.path.join(storage_dir, f"{doc_id}_bm25.hrb"), os.path.join(storage_dir, f"{doc_id}_vocab.json"))
+
+
+def build_bm25_sidecar(doc_id: str, chunk_texts: List[str], storage_dir: Optional[str] = None):
+    """Ingest side: tokenise every chunk with the reference's idiom (``text.lower().split()``,
+    rag/agent/query_processor.py:26), build the BM25 index on the GPU (row i of the faiss index == doc i)
+    and write ``{doc_id}_bm25.hrb`` + ``{doc_id}_vocab.json`` next to ``{doc_id}_faiss.index``.
+    Returns (BM25Index, Vocabulary)."""
+    from .bm25 import BM25Index, Vocabulary
+    storage_dir = str(storage_dir or os.environ.get("STORAGE_DIR", config.STORAGE_DIR))
+    vocab = Vocabulary()
+    docs = [vocab.encode(t, grow=True) for t in chunk_texts]
+    index = BM25Index.from_docs(docs, max(len(vocab), 1))
+    bm_path, vocab_path = _sidecar_paths(storage_dir, doc_id)
+    index.save(bm_path)
+    with open(vocab_path, "w", encoding="utf-8") as f:
+        json.dump({"n_docs": len(docs), "words": list(vocab.word_to_id.keys())}, f, ensure_ascii=False)
+    logger.info("Saved BM25 sidecar: %s (%d docs, %d terms)", bm_path, len(docs), len(vocab))
+    return index, vocab
+
+
+def _load_bm25_sidecar(storage_dir: str, doc_id: str):
+    from .bm25 import BM25Index, Vocabulary
+    bm_path, vocab_path = _sidecar_paths(storage_dir, doc_id)
+    if not (os.path.exists(bm_path) and os.path.exists(vocab_path)):
+        return None
+    key = (bm_path, _mtime(bm_path))
+    hit = _BM25_CACHE.get(key)
+    if hit is not None:
+        return hit
+    with open(vocab_path, "r", encoding="utf-8") as f:
+        words = json.load(f)["words"]
+    vocab = Vocabulary()
+    vocab.word_to_id = {w: i for i, w in enumerate(words)}
+    pair = (BM25Index.load(bm_path), vocab)
+    for old in [k for k in _BM25_CACHE if k[0] == bm_path]:
+        del _BM25_CACHE[old]
+    _BM25_CACHE[key] = pair
+    return pair
+
+
+async def search_hybrid_by_vector(query_vector: List[float], query_text: str, limit: int = 10,
+                                  project: Optional[str] = None) -> List[dict]:
+    """Hybrid variant of `search_faiss_by_vector`: dense + BM25 + weighted fusion (weights and defaults from
+    rag/config.py:41-45) over the first ``*_faiss.index`` and its BM25 sidecar; without a sidecar it is the
+    dense search.  `score` is the fused score; hits carry the same chunk metadata keys."""
+    from .retriever import HybridRetriever
+    storage_dir = str(os.environ.get("STORAGE_DIR", config.STORAGE_DIR))
+    index_files = sorted(glob.glob(os.path.join(storage_dir, "*_faiss.index")))
+    if not index_files:
+        logger.warning("No FAISS indices found")
+        return []
+    index_path = index_files[0]
+    reader = FAISSIndexReader(index_path)
+    doc_id = os.path.basename(index_path)[: -len(".index")].replace("_faiss", "")
+    side = _load_bm25_sidecar(storage_dir, doc_id) if config.HYBRID_SEARCH_ENABLED else None
+    q = np.array([query_vector], dtype=np.float32)
+    limit = int(limit)
+    if side is None:
+        engine, tokens = HybridRetriever(reader.index, None), None
+    else:
+        engine, tokens = HybridRetriever(reader.index, side[0]), [side[1].encode(query_text or "")]
+    scores, ids = engine.retrieve(q, tokens, top_k=limit, k_c=min(128, max(limit, config.CANDIDATE_DEPTH)))
+    chunks = _load_chunk_list(storage_dir, doc_id)
+    out = []
+    for row, score in zip(ids[0], scores[0]):
+        row = int(row)
+        if 0 <= row < len(chunks):
+            c = chunks[row]
+            meta = c.get("metadata", {})
+            out.append({
+                "chunk_id": c.get("chunk_id", f"unknown_{row}"),
+                "text": c.get("text", ""),
+                "score": float(score),
+                "page": c.get("page", 0),
+                "chapter": meta.get("chapter"),
+                "section": meta.get("section"),
+                "subsection": meta.get("subsection"),
+                "title": meta.get("title"),
+                "source_filename": meta.get("source_filename"),
+            })
+    logger.info("Hybrid search returned %d results", len(out))
+    return out

@@ -70,3 +70,36 @@ def test_search_faiss_by_vector_matches_reference_run(gpu, golden, tmp_path, mon
 def test_empty_storage_returns_empty(gpu, tmp_path, monkeypatch):
     monkeypatch.setenv("STORAGE_DIR", str(tmp_path))
     assert asyncio.run(storage.search_faiss_by_vector([0.0] * 4, limit=3)) == []
+
+
+def test_hybrid_service_path_with_bm25_sidecar(gpu, golden, tmp_path, monkeypatch):
+    """build_bm25_sidecar + search_hybrid_by_vector == the oracle's hybrid retrieve on the same chunks."""
+    from oracle import bm25 as obm25, flat, hybrid
+    z, g = golden
+    _setup_storage(tmp_path, z, g, monkeypatch)
+    sd = str(tmp_path / "storages")
+    n = g["n"]
+    rng = np.random.default_rng(5)
+    words = [f"w{i}" for i in range(60)]
+    texts = [" ".join(rng.choice(words, size=int(rng.integers(5, 30)))) + f" Chunk{i % 7}" for i in range(n)]
+    chunks = [{"chunk_id": f"c_{i}", "page": i // 4 + 1, "text": texts[i], "chunk_index": i} for i in range(n)]
+    open(os.path.join(sd, f"{g['doc_id']}_chunks.json"), "w").write(json.dumps({"total": n, "chunks": chunks}))
+    bm, vocab = storage.build_bm25_sidecar(g["doc_id"], texts, storage_dir=sd)
+    assert bm.ndocs == n and os.path.exists(os.path.join(sd, f"{g['doc_id']}_bm25.hrb"))
+    # oracle on the same tokenisation
+    docs = [vocab.encode(t) for t in texts]
+    oc = obm25.BM25Corpus(docs, len(vocab))
+    oi = flat.IndexFlatL2(g["d"])
+    oi.add(z["x"])
+    for qi, qv in enumerate(z["queries"][:4]):
+        text = f"W3 w17 chunk{qi} w17 unknownword"
+        got = asyncio.run(storage.search_hybrid_by_vector(list(map(float, qv)), text, limit=8))
+        Sr, Ir, _ = hybrid.retrieve(oi, oc, qv[None, :], [vocab.encode(text)], 8)
+        keep = Ir[0] >= 0
+        assert [h["chunk_id"] for h in got] == [f"c_{i}" for i in Ir[0][keep]]
+        np.testing.assert_allclose([h["score"] for h in got], Sr[0][keep], rtol=2e-5, atol=1e-6)
+    # no sidecar -> dense only, same ids as the dense search
+    os.remove(os.path.join(sd, f"{g['doc_id']}_bm25.hrb"))
+    got = asyncio.run(storage.search_hybrid_by_vector(list(map(float, z["queries"][0])), "w3", limit=5))
+    dense = asyncio.run(storage.search_faiss_by_vector(list(map(float, z["queries"][0])), limit=5))
+    assert [h["chunk_id"] for h in got] == [h["chunk_id"] for h in dense]
