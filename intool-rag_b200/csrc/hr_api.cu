@@ -440,7 +440,13 @@ static int list_len_for_k(int k) {
 template <typename T>
 static int launch_exact(hr_index* h, const int* qsel_dev, int nsel, int k, float* D, int64_t* I, cudaStream_t st) {
   // exhaustive exact scan of the queries listed in qsel_dev (device), results written to D/I rows qsel[i]
-  const int grid = h->num_sms;
+  // warps in flight set the memory-level parallelism of this row-per-warp scan: as many CTAs per SM as the
+  // query tile in shared memory allows, up to 2 (measured at 10M x 1024: 39 / 28 / 35 ms per 8 queries with 1 / 2 / 4);
+  // k is up to 2048, so the per-warp lists bound it as well
+  const size_t smem_q = (size_t)kExactF * h->ld * 4;
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / std::max<size_t>(smem_q, 1)));
+  if (k > 256) per_sm = 1;
+  const int grid = h->num_sms * per_sm;
   const int64_t W = (int64_t)grid * 8;
   int fsel = std::max(kExactF, std::min(64, (64 * 128 / std::max(k, 1)) / kExactF * kExactF));
   HR_TRY(h->ex_lists.ensure((size_t)fsel * W * k * 8));
