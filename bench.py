@@ -267,19 +267,22 @@ def run_b200(args):
         """K steps bracketed by barrier + synchronize; CUDA events on the launch stream; max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        scan_ms, flagged = 0.0, 0
+        scan_ms, flagged, deeper = 0.0, 0, 0
         e0.record()
         for _ in range(steps):
             fn()
             st = ix.stats()
             scan_ms += st["scan_ms"]
             flagged += st["flagged"]
+            deeper += st["deeper"]
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        cnt = torch.tensor([flagged, deeper], device=dev, dtype=torch.int64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), scan_ms / steps, flagged
+            dist.all_reduce(cnt)     # fallbacks on ANY rank stall every rank at the all-gather
+        return float(ms.item()), scan_ms / steps, (int(cnt[0].item()), int(cnt[1].item()))
 
     for _ in range(max(args.warmup, 3)):
         out = step_dev()
@@ -360,7 +363,8 @@ def run_b200(args):
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roofline,
-            "fallback_queries_in_timed_region": int(flagged), "parity_check": check}
+            "fallback_queries_in_timed_region": int(flagged[0]),
+            "second_stage_rescore_queries_in_timed_region": int(flagged[1]), "parity_check": check}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(args, steps=1, warmup=1)
     if args.sweep and world == 1:

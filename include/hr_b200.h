@@ -66,6 +66,7 @@ typedef struct hr_scan_stats {
   int mode_used;            /* HR_MODE_* actually taken                                  */
   int list_len;             /* per-CTA candidate list length used by the filter          */
   int grid;                 /* CTAs of the scan kernel                                   */
+  int deeper;               /* queries certified only after re-scoring all their candidates */
 } hr_scan_stats;
 
 /* ---- library ----------------------------------------------------------------------- */

@@ -25,7 +25,7 @@ MAX_K = 2048
 class ScanStats(C.Structure):
     _fields_ = [("launches", C.c_int64), ("flagged", C.c_int64), ("overflow", C.c_int64),
                 ("scan_ms", C.c_float), ("total_ms", C.c_float), ("mode_used", C.c_int),
-                ("list_len", C.c_int), ("grid", C.c_int)]
+                ("list_len", C.c_int), ("grid", C.c_int), ("deeper", C.c_int)]
 
 
 # every symbol include/hr_b200.h declares: name -> (restype, argtypes)

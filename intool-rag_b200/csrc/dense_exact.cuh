@@ -325,22 +325,28 @@ exact_merge_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
 }
 
 // ---- exact re-score of the filter shortlist + final top-k + certificate ---------------------------
-// One block (256 threads) per query.  short_rows [nq][KL] (0xFFFFFFFF = empty), short_n [nq],
+// Two stages.  Stage 1 (qsel == nullptr, one block per query): the best short_n <= KL candidates.  A query
+// whose certificate fails while more candidates exist (short_tot > short_n) goes to the `deeper` list; stage 2
+// (qsel = that list, KL = row_stride) re-scores ALL its candidates against the bound of the thresholds alone.
+// Only what still fails is flagged for the exhaustive exact scan.
+// One block (256 threads) per query.  short_rows [nq][row_stride] (0xFFFFFFFF = empty), short_n [nq],
 // tprime [nq] = upper bound on the APPROXIMATE score of every row that is not in the shortlist
 // (HR_NEG_INF when nothing was dropped).  A query is certified when its exact k-th best, mapped to
 // the filter's score domain, beats tprime by more than the filter's worst-case error eps.
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(256)
 rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict__ qpad,
-                        const uint32_t* __restrict__ short_rows, const int* __restrict__ short_n,
+                        const uint32_t* __restrict__ short_rows, int row_stride, const int* __restrict__ short_n,
                         const float* __restrict__ tprime, int KL, int k, float c_acc, int filter_kind,
                         const unsigned int* __restrict__ max_norm2_ord, int64_t id_base, float* __restrict__ D,
-                        int64_t* __restrict__ I, int* __restrict__ flagged, int* __restrict__ nflag) {
+                        int64_t* __restrict__ I, int* __restrict__ flagged, int* __restrict__ nflag,
+                        const int* __restrict__ qsel, const int* __restrict__ short_tot, int* __restrict__ deeper,
+                        int* __restrict__ ndeeper) {
   extern __shared__ uint64_t skeys[];  // [KL]
   __shared__ float s_qn2, s_dq2, s_qt2;
   __shared__ float s_ek;
   __shared__ int s_have_k;
-  const int q = blockIdx.x;
+  const int q = qsel ? qsel[blockIdx.x] : blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarp = blockDim.x >> 5;
@@ -366,7 +372,7 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
     }
   }
   for (int i = warp; i < n; i += nwarp) {
-    uint32_t row = short_rows[(int64_t)q * KL + i];
+    uint32_t row = short_rows[(int64_t)q * row_stride + i];
     float sc[1];
     warp_exact_scores<T, METRIC, 1>(x + (int64_t)row * ld, qv, ld, ld, lane, sc);
     if (lane == 0) skeys[i] = make_key(METRIC == kMetricIP ? sc[0] : -sc[0], row);
@@ -414,8 +420,13 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
       ok = shat > tp + eps;
     }
     if (!ok) {
-      int slot = atomicAdd(nflag, 1);
-      flagged[slot] = q;
+      if (deeper && short_tot[q] > n) {
+        int slot = atomicAdd(ndeeper, 1);
+        deeper[slot] = q;
+      } else {
+        int slot = atomicAdd(nflag, 1);
+        flagged[slot] = q;
+      }
     }
   }
 }

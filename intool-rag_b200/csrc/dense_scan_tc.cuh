@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(256)
 scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
                   const unsigned int* __restrict__ tau_g, int G, int nq, int KL,
                   uint32_t* __restrict__ short_rows, int* __restrict__ short_n, float* __restrict__ tprime,
-                  int* __restrict__ overflow_count, unsigned int* __restrict__ tau_seed) {
+                  int* __restrict__ overflow_count, unsigned int* __restrict__ tau_seed,
+                  int* __restrict__ short_tot, float* __restrict__ tprime_tot) {
   __shared__ uint64_t buf[kShortCap];
   __shared__ int s_n;
   __shared__ int hist[256];
@@ -572,10 +573,14 @@ scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
     }
     n = merge_compact(lists, cnts, G, nq, KL, q, tstar, s_prefix, buf, &s_n);
   }
-  uint32_t* out = short_rows + (size_t)q * KL;
+  // rows are written best first with stride kShortCap: the first KL are the stage-1 shortlist, the rest (every
+  // candidate that survived the thresholds) is only re-scored if the certificate fails on the first KL
+  uint32_t* out = short_rows + (size_t)q * kShortCap;
   if (n > kShortCap) {  // massive exact ties at the KL-th score: cannot rank -> exact fallback
     if (threadIdx.x == 0) {
       short_n[q] = 0;
+      short_tot[q] = 0;
+      tprime_tot[q] = -HR_NEG_INF;
       tprime[q] = -HR_NEG_INF;
       if (tau_seed) tau_seed[q] = o;
       else atomicAdd(overflow_count, 1);
@@ -587,9 +592,14 @@ scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
   while (pw < n) pw <<= 1;
   for (int i = n + threadIdx.x; i < pw; i += blockDim.x) buf[i] = 0;
   block_bitonic_desc(buf, pw);
-  for (int j = threadIdx.x; j < KL; j += blockDim.x) out[j] = (j < n) ? key_row(buf[j]) : 0xFFFFFFFFu;
+  for (int j = threadIdx.x; j < max(KL, n); j += blockDim.x) out[j] = (j < n) ? key_row(buf[j]) : 0xFFFFFFFFu;
   if (threadIdx.x == 0) {
     short_n[q] = n < KL ? n : KL;
+    short_tot[q] = n;
+    // bound on the approximate score of every row outside the n candidates: the final threshold (or the radix cut)
+    float tt = o ? tstar : HR_NEG_INF;
+    if (radix && n > 0) tt = fmaxf(tt, key_score(buf[n - 1]));
+    tprime_tot[q] = tt;
     float tp = HR_NEG_INF;
     if (o) tp = tstar;                                  // rows dropped by a threshold are <= T*
     if (n > KL) tp = fmaxf(tp, key_score(buf[KL]));     // best compacted entry that was left out
@@ -602,34 +612,23 @@ scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
 }
 
 // ---- threshold seed from the pre-pass ---------------------------------------------------------------
-// pre_max [T][nq]: the best filter score of each of T sampled tiles (each the score of a distinct corpus
-// row).  The j-th largest of them is <= the j-th best score of the sample, whose rank in the corpus is about
-// j * stride: a valid, deliberately loose lower bound of the query's KL-th best.  One warp per query.
+// pre_max [T][nq]: the best filter score of each of T <= kSeedCap sampled tiles (each the score of a distinct
+// corpus row).  The j-th largest of them is <= the j-th best score of the sample; its rank R in the corpus is
+// Gamma(j, stride) distributed (mean j * stride, relative spread 1/sqrt(j)): with j >= 32 the seed is both close
+// to its target rank and, for all practical purposes, never inside the true top KL.  One block per query.
+constexpr int kSeedCap = 2048;
 __global__ void __launch_bounds__(256)
 scan_seed_kernel(const float* __restrict__ pre_max, int T, int nq, int j, unsigned int* __restrict__ tau_g) {
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (q >= nq) return;
-  // value with exactly j-1 ... values above it under the total order (value desc, tile asc): rank by counting
-  float seed = HR_NEG_INF;
-  bool found = false;
-  for (int a = lane; a < ((T + 31) & ~31); a += 32) {
-    const float va = a < T ? pre_max[(size_t)a * nq + q] : HR_NEG_INF;
-    int rank = 0;
-    if (a < T)
-      for (int b = 0; b < T; ++b) {
-        const float vb = pre_max[(size_t)b * nq + q];
-        rank += (vb > va) || (vb == va && b < a);
-      }
-    if (a < T && rank == j - 1) {
-      seed = va;
-      found = true;
-    }
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, found);
-  if (m) {
-    seed = __shfl_sync(0xffffffffu, seed, __ffs(m) - 1);
-    if (lane == 0 && seed > HR_NEG_INF) tau_g[q] = f2ord(seed);
+  __shared__ uint64_t buf[kSeedCap];
+  const int q = blockIdx.x;
+  int pw = 1;
+  while (pw < T) pw <<= 1;
+  for (int i = threadIdx.x; i < pw; i += blockDim.x)
+    buf[i] = i < T ? make_key(pre_max[(size_t)i * nq + q], (uint32_t)i) : 0ull;
+  block_bitonic_desc(buf, pw);
+  if (threadIdx.x == 0) {
+    const uint64_t key = buf[min(j, T) - 1];
+    if (key != 0ull && key_score(key) > HR_NEG_INF) tau_g[q] = (uint32_t)(key >> 32);
   }
 }
 

@@ -176,9 +176,10 @@ struct hr_index {
   __nv_bfloat16* xs = nullptr;  // F32_SHADOW16 only: bf16 copy of the rows for the tensor-core filter, [capacity][ld]
   float* norms = nullptr;
   unsigned int* max_norm2 = nullptr;  // ordered-uints: [0] max |x|^2, [1] max |x - filter's view of x|^2
-  DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_n, tprime, flagged, counters, pre_max;
+  DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_n, short_tot, tprime, tprime_tot, flagged, deeper, counters,
+      pre_max;
   DevBuf ex_lists, ex_cnts, ex_tau, ex_sel, io_q, io_D, io_I, stage;
-  int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow
+  int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow [2]=ndeeper
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   hr_scan_stats stats{};
 };
@@ -257,7 +258,7 @@ extern "C" int hr_index_destroy(hr_index* h) {
   if (h->max_norm2) cudaFree(h->max_norm2);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   DevBuf* bufs[] = {&h->qpad, &h->qh, &h->lists, &h->cnts, &h->tau_g, &h->short_rows, &h->short_n, &h->tprime,
-                    &h->flagged, &h->counters, &h->pre_max, &h->ex_lists, &h->ex_cnts, &h->ex_tau, &h->ex_sel, &h->io_q,
+                    &h->flagged, &h->counters, &h->pre_max, &h->short_tot, &h->tprime_tot, &h->deeper, &h->ex_lists, &h->ex_cnts, &h->ex_tau, &h->ex_sel, &h->io_q,
                     &h->io_D, &h->io_I, &h->stage, &h->rs.q, &h->rs.qi, &h->rs.qt, &h->rs.dD, &h->rs.dI,
                     &h->rs.bS, &h->rs.bI, &h->rs.oS, &h->rs.oI};
   for (DevBuf* b : bufs) b->release();
@@ -389,7 +390,9 @@ extern "C" int hr_index_debug_dump(hr_index* h, int64_t nq, void* lists, int32_t
   if (lists) HR_CUDA(cudaMemcpy(lists, h->lists.p, (size_t)G * nq * KL * sizeof(Cand), cudaMemcpyDeviceToHost));
   if (cnts) HR_CUDA(cudaMemcpy(cnts, h->cnts.p, (size_t)G * nq * 4, cudaMemcpyDeviceToHost));
   if (tau) HR_CUDA(cudaMemcpy(tau, h->tau_g.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
-  if (short_rows) HR_CUDA(cudaMemcpy(short_rows, h->short_rows.p, (size_t)nq * KL * 4, cudaMemcpyDeviceToHost));
+  if (short_rows)
+    HR_CUDA(cudaMemcpy2D(short_rows, (size_t)KL * 4, h->short_rows.p, (size_t)kShortCap * 4, (size_t)KL * 4, (size_t)nq,
+                         cudaMemcpyDeviceToHost));
   if (tprime) HR_CUDA(cudaMemcpy(tprime, h->tprime.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
   return HR_OK;
 }
@@ -504,20 +507,30 @@ static int launch_scan2(hr_index* h, const CUtensorMap& tq, const CUtensorMap& t
   return HR_OK;
 }
 
+// stage 1: every query of the batch, the best KL candidates; stage 2: the `ndeeper` queries listed in h->deeper,
+// all their candidates (up to kShortCap) against the bound of the thresholds alone
 template <typename T>
-static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_acc, float* D, int64_t* I, cudaStream_t st) {
+static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_acc, float* D, int64_t* I, cudaStream_t st,
+                          int ndeeper = 0) {
   const int fk = filter_is_bf16(h) ? 2 : 1;   // how the filter rounded the query
-  const size_t smem = (size_t)KL * 8;
+  const bool stage2 = ndeeper > 0;
+  const int depth = stage2 ? kShortCap : KL;
+  const int blocks = stage2 ? ndeeper : nb;
+  const size_t smem = (size_t)depth * 8;
+  const int* n_in = stage2 ? h->short_tot.as<int>() : h->short_n.as<int>();
+  const float* tp = stage2 ? h->tprime_tot.as<float>() : h->tprime.as<float>();
+  const int* qsel = stage2 ? h->deeper.as<int>() : nullptr;
+  int* deeper = stage2 ? nullptr : h->deeper.as<int>();
   if (h->metric == HR_METRIC_INNER_PRODUCT)
-    rescore_finalize_kernel<T, kMetricIP><<<nb, 256, smem, st>>>(
-        (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
-        h->tprime.as<float>(), KL, k, c_acc, fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(),
-        h->counters.as<int>());
+    rescore_finalize_kernel<T, kMetricIP><<<blocks, 256, smem, st>>>(
+        (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), kShortCap, n_in, tp, depth, k, c_acc,
+        fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(), h->counters.as<int>(), qsel,
+        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2);
   else
-    rescore_finalize_kernel<T, kMetricL2><<<nb, 256, smem, st>>>(
-        (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
-        h->tprime.as<float>(), KL, k, c_acc, fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(),
-        h->counters.as<int>());
+    rescore_finalize_kernel<T, kMetricL2><<<blocks, 256, smem, st>>>(
+        (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), kShortCap, n_in, tp, depth, k, c_acc,
+        fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(), h->counters.as<int>(), qsel,
+        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2);
   HR_LAUNCHED();
   return HR_OK;
 }
@@ -575,7 +588,10 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     HR_TRY(h->lists.ensure((size_t)h->num_sms * nb * KL * sizeof(Cand)));
     HR_TRY(h->cnts.ensure((size_t)h->num_sms * nb * 4));
     HR_TRY(h->tau_g.ensure((size_t)nb * 4));
-    HR_TRY(h->short_rows.ensure((size_t)nb * KL * 4));
+    HR_TRY(h->short_rows.ensure((size_t)nb * kShortCap * 4));
+    HR_TRY(h->short_tot.ensure((size_t)nb * 4));
+    HR_TRY(h->tprime_tot.ensure((size_t)nb * 4));
+    HR_TRY(h->deeper.ensure((size_t)nb * 4));
     HR_TRY(h->short_n.ensure((size_t)nb * 4));
     HR_TRY(h->tprime.ensure((size_t)nb * 4));
     HR_TRY(h->flagged.ensure((size_t)nb * 4));
@@ -622,25 +638,26 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     //      seeds tau_g: about KLs*stride (= 4*KL) corpus rows beat it, so in the main pass only a handful
     //      of scores per CTA pass the threshold and no per-CTA list ever fills.  Correctness never depends
     //      on the seed: the certificate in rescore_finalize compares against the final threshold. ----
-    // Sample size: four tiles per scheduling unit (CTA or CTA pair), so the pre-pass is one short balanced wave.
+    // Sample: at least pre_tiles tiles per scheduling unit (CTA or CTA pair) and at least every 32nd tile, at most
+    // kSeedCap tiles.  The seed is the j-th largest tile maximum, j >= 32: its corpus rank is Gamma(j, stride)
+    // distributed, mean about pre_rank * KL (or 32 * stride if that is larger), spread 1/sqrt(j).  A seed taken
+    // from fewer maxima (j = 8) landed inside the top 100 rows of a 5M-row shard for about 1 query in 10^4 and sent
+    // it to the exact scan: 16 ms for one query.
     const int units = use_pair ? std::max(1, h->num_sms / 2) : h->num_sms;
-    const int tpu = tuning().pre_tiles;   // sampled tiles per unit
-    const int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (tpu * units)));
+    int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (tuning().pre_tiles * units)));
+    stride = std::min(stride, 32);
+    stride = std::max(stride, (num_ctiles + kSeedCap - 1) / kSeedCap);
     if (stride > 1) {
-      // the j-th largest tile maximum ranks about j*stride in the corpus: about 2*KL (a tighter seed means
-      // fewer list insertions in the main pass); if it lands inside the true top KL the shortlist is
-      // shorter and the certificate compares against the seed itself, which still sits far below rank k
       p.tile_stride = stride;
       p.tile_count = (num_ctiles + stride - 1) / stride;
       const int rk = tuning().pre_rank;   // target rank of the seed, in KL
-      const int jth = std::min(p.tile_count, std::max(rk >= 4 ? 10 : 8, (rk * KL + stride - 1) / stride));
+      const int jth = std::min(p.tile_count, std::max(32, (rk * KL + stride - 1) / stride));
       HR_TRY(h->pre_max.ensure((size_t)p.tile_count * nb * 4));
       p.pre_max = h->pre_max.as<float>();
       const int gs = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1)
                               : std::min(p.tile_count, h->num_sms);
       HR_TRY(run_scan(gs));
-      scan_seed_kernel<<<(nb + 7) / 8, 256, 0, st>>>(h->pre_max.as<float>(), p.tile_count, nb, jth,
-                                                     h->tau_g.as<unsigned int>());
+      scan_seed_kernel<<<nb, 256, 0, st>>>(h->pre_max.as<float>(), p.tile_count, nb, jth, h->tau_g.as<unsigned int>());
       HR_LAUNCHED();
       p.pre_max = nullptr;
     }
@@ -653,15 +670,24 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     h->stats.grid = gmain;
     scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), gmain,
                                           nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
-                                          h->tprime.as<float>(), h->counters.as<int>() + 1, nullptr);
+                                          h->tprime.as<float>(), h->counters.as<int>() + 1, nullptr,
+                                          h->short_tot.as<int>(), h->tprime_tot.as<float>());
     HR_LAUNCHED();
     // filter error bound = measured rounding residuals of both operands (rescore_finalize_kernel) + this
     // relative allowance for the fp32 accumulation over ld terms
     const float c_acc = 2.4e-7f * (float)h->ld;
     if (h->elem == 4) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_acc, Db, Ib, st));
     else HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_acc, Db, Ib, st));
-    HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 8, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 12, cudaMemcpyDeviceToHost, st));
     HR_CUDA(cudaStreamSynchronize(st));
+    if (h->h_counters[2] > 0) {
+      // certificate failed on the best KL candidates of a few queries: re-score all their candidates
+      h->stats.deeper += h->h_counters[2];
+      if (h->elem == 4) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_acc, Db, Ib, st, h->h_counters[2]));
+      else HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_acc, Db, Ib, st, h->h_counters[2]));
+      HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 8, cudaMemcpyDeviceToHost, st));
+      HR_CUDA(cudaStreamSynchronize(st));
+    }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) scan_ms_total += ms;
     const int nflag = h->h_counters[0];

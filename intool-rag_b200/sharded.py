@@ -92,9 +92,12 @@ class ShardedRetriever:
         n = nq * kc
         key = (nq, kc, world)
         if key not in self._bufs:
-            self._bufs = {key: (torch.empty(24 * n, dtype=torch.uint8, device=dev),
-                                torch.empty(world * 24 * n, dtype=torch.uint8, device=dev))}
-        local, gathered = self._bufs[key]
+            local = torch.empty(24 * n, dtype=torch.uint8, device=dev)
+            gathered = torch.empty(world * 24 * n, dtype=torch.uint8, device=dev) if world > 1 else local
+            # raw pointers of the four lists of the local block and of rank 0's block of the gathered buffer
+            self._bufs = {key: (local, gathered, [v.data_ptr() for v in self._views(local, n)],
+                                [v.data_ptr() for v in self._views(gathered, n)])}
+        local, gathered, lp, gp = self._bufs[key]
         use_bm = self.bm25 is not None and query_tokens is not None
         qi = qt = None
         if use_bm:
@@ -108,20 +111,16 @@ class ShardedRetriever:
                 raise AssertionError("retrieve: query_tokens and query_embeddings disagree on nq")
         L = _lib.lib()
         st = _lib.current_stream_ptr(self.index.device)
-        D, S, I, J = self._views(local, n)
-        _lib.check(L.hr_candidates(self.index._h, self.bm25._h if use_bm else None, q.data_ptr(),
-                                   qi.data_ptr() if use_bm else None, qt.data_ptr() if use_bm else None, nq,
-                                   int(qt.numel()) if use_bm else 0, kc, D.data_ptr(), I.data_ptr(), S.data_ptr(),
-                                   J.data_ptr(), st))
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, local, group=self.group)
-            src = gathered
-        else:
-            src = local
-        D, S, I, J = self._views(src, n)
+        # outputs first: hr_candidates returns after a stream synchronisation, nothing but the all-gather and the
+        # merge launch should stand between that point and the GPU's next kernel
         oS = torch.empty((nq, top_k), dtype=torch.float32, device=dev)
         oI = torch.empty((nq, top_k), dtype=torch.int64, device=dev)
-        _lib.check(L.hr_merge_fuse_lists(self.index._h, D.data_ptr(), I.data_ptr(), S.data_ptr(), J.data_ptr(), world,
-                                         24 * n, nq, kc, top_k, _MODES[self.fusion], self.vector_weight,
-                                         self.bm25_weight, oS.data_ptr(), oI.data_ptr(), st))
+        _lib.check(L.hr_candidates(self.index._h, self.bm25._h if use_bm else None, q.data_ptr(),
+                                   qi.data_ptr() if use_bm else None, qt.data_ptr() if use_bm else None, nq,
+                                   int(qt.numel()) if use_bm else 0, kc, lp[0], lp[2], lp[1], lp[3], st))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local, group=self.group)
+        _lib.check(L.hr_merge_fuse_lists(self.index._h, gp[0], gp[2], gp[1], gp[3], world, 24 * n, nq, kc, top_k,
+                                         _MODES[self.fusion], self.vector_weight, self.bm25_weight, oS.data_ptr(),
+                                         oI.data_ptr(), st))
         return oS, oI
