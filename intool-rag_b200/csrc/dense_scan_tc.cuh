@@ -537,11 +537,11 @@ scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
   int n = merge_compact(lists, cnts, G, nq, KL, q, tstar, 0u, buf, &s_n);
   bool radix = false;
   if (n > kShortCap) {
-    // exact KL-th largest ordered score among the entries >= T*  (MSB-first radix select)
+    // exact m-th largest ordered score among the entries >= T*, m = max(KL, 1024)  (MSB-first radix select)
     radix = true;
     if (threadIdx.x == 0) {
       s_prefix = 0;
-      s_remaining = KL;
+      s_remaining = max(KL, kShortCap / 2);   // keep a deep candidate set for the second re-score stage
     }
     const int total = G * KL;
     for (int shift = 24; shift >= 0; shift -= 8) {

@@ -125,6 +125,31 @@ def test_duplicates_force_fallback_and_keep_tie_rule(gpu):
     assert I[0].tolist() == [17] + list(range(1000, 1009)) and np.allclose(D, 0, atol=1e-6)
 
 
+@pytest.mark.parametrize("storage", ["f32", "f32+bf16"])
+def test_near_duplicates_take_the_second_rescore_stage(gpu, storage):
+    """200 rows within 1e-4 of each other, scattered over the corpus, next to the query: the filter cannot
+    separate rank 10 from rank KL, but every candidate above the thresholds fits the deep shortlist, so the second
+    re-score stage certifies the query without the exhaustive exact scan; the answer equals the exact scan bit for
+    bit.  (The same rows stored contiguously fill one CTA's list, push the threshold into the cluster and
+    rightly end in the exact scan: test_duplicates_force_fallback_and_keep_tie_rule.)"""
+    d = 256
+    rng = np.random.default_rng(8)
+    x = synth.dense_corpus_np(60000, d)
+    base = x[123].copy()
+    where = np.sort(rng.choice(np.arange(1000, 60000), size=200, replace=False))
+    x[where] = base + 1e-4 * rng.standard_normal((200, d)).astype(np.float32)
+    q = np.concatenate([base[None, :], synth.dense_queries_np(x, 40)]).astype(np.float32)
+    ix = _mk("ip", d, storage=storage)
+    ix.add(x)
+    D, I = ix.search(q, 10)
+    st = ix.stats()
+    assert st["deeper"] >= 1 and st["flagged"] == 0, st
+    ix.set_mode("exact")
+    De, Ie = ix.search(q, 10)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De)
+    assert set(I[0]) <= set(where.tolist()) | {123}
+
+
 @pytest.mark.parametrize("d", [1, 3, 31, 100, 384, 1000])
 def test_odd_dimensions(gpu, d):
     rng = np.random.default_rng(d)
