@@ -41,22 +41,37 @@ __device__ __forceinline__ void warp_exact_scores(const T* __restrict__ xrow, co
   float acc[F];
 #pragma unroll
   for (int f = 0; f < F; ++f) acc[f] = 0.f;
-  for (int c = lane * 4; c < ld; c += 128) {
-    float4 xv = load4<T>(xrow + c);
+  // up to eight 16-byte loads of the row in flight per lane before the first use (the chain order per lane is unchanged:
+  // elements in increasing c)
+  constexpr int U = F <= 2 ? 8 : 1;   // batch variant (F = 8): registers go to the accumulators instead
+  for (int c0 = lane * 4; c0 < ld; c0 += 128 * U) {
+    float4 xv4[U];
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-      float4 qv = *reinterpret_cast<const float4*>(q + (size_t)f * q_stride + c);
-      if (METRIC == kMetricIP) {
-        acc[f] = fmaf(xv.x, qv.x, acc[f]);
-        acc[f] = fmaf(xv.y, qv.y, acc[f]);
-        acc[f] = fmaf(xv.z, qv.z, acc[f]);
-        acc[f] = fmaf(xv.w, qv.w, acc[f]);
-      } else {
-        float d0 = xv.x - qv.x, d1 = xv.y - qv.y, d2 = xv.z - qv.z, d3 = xv.w - qv.w;
-        acc[f] = fmaf(d0, d0, acc[f]);
-        acc[f] = fmaf(d1, d1, acc[f]);
-        acc[f] = fmaf(d2, d2, acc[f]);
-        acc[f] = fmaf(d3, d3, acc[f]);
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + 128 * u;
+      xv4[u] = c < ld ? load4<T>(xrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + 128 * u;
+      if (c < ld) {
+        const float4 xv = xv4[u];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          float4 qv = *reinterpret_cast<const float4*>(q + (size_t)f * q_stride + c);
+          if (METRIC == kMetricIP) {
+            acc[f] = fmaf(xv.x, qv.x, acc[f]);
+            acc[f] = fmaf(xv.y, qv.y, acc[f]);
+            acc[f] = fmaf(xv.z, qv.z, acc[f]);
+            acc[f] = fmaf(xv.w, qv.w, acc[f]);
+          } else {
+            float d0 = xv.x - qv.x, d1 = xv.y - qv.y, d2 = xv.z - qv.z, d3 = xv.w - qv.w;
+            acc[f] = fmaf(d0, d0, acc[f]);
+            acc[f] = fmaf(d1, d1, acc[f]);
+            acc[f] = fmaf(d2, d2, acc[f]);
+            acc[f] = fmaf(d3, d3, acc[f]);
+          }
+        }
       }
     }
   }
@@ -181,31 +196,33 @@ __device__ __forceinline__ void warp_list_insert(volatile uint64_t* list, int k,
   }
 }
 
-template <typename T, int METRIC>
+// F = queries scored per corpus pass: 8 for a batch (HR_MODE_EXACT_SIMT), 2 when only one or two queries
+// need the fallback (a pass is then bound by HBM, not by shared-memory reads of six idle query slots).
+template <typename T, int METRIC, int F>
 __global__ void __launch_bounds__(256)
 exact_scan_kernel(const T* __restrict__ x, int64_t N, int ld, const float* __restrict__ qpad,
                   const int* __restrict__ qsel, int nsel, int k, uint64_t* __restrict__ lists,
                   int* __restrict__ cnts, unsigned long long* __restrict__ tau_g) {
-  extern __shared__ __align__(16) float qs[];  // [kExactF][ld]
+  extern __shared__ __align__(16) float qs[];  // [F][ld]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int64_t W = (int64_t)gridDim.x * wpb;
   const int64_t gw = (int64_t)blockIdx.x * wpb + wib;
 
-  for (int g0 = 0; g0 < nsel; g0 += kExactF) {
-    const int nf = min(kExactF, nsel - g0);
+  for (int g0 = 0; g0 < nsel; g0 += F) {
+    const int nf = min(F, nsel - g0);
     __syncthreads();
-    for (int i = threadIdx.x; i < kExactF * ld; i += blockDim.x) {
+    for (int i = threadIdx.x; i < F * ld; i += blockDim.x) {
       int f = i / ld, c = i - f * ld;
       qs[i] = (f < nf) ? qpad[(int64_t)qsel[g0 + f] * ld + c] : 0.f;
     }
     __syncthreads();
 
-    int cnt[kExactF];
-    uint64_t minkey[kExactF], tg[kExactF];
+    int cnt[F];
+    uint64_t minkey[F], tg[F];
 #pragma unroll
-    for (int f = 0; f < kExactF; ++f) {
+    for (int f = 0; f < F; ++f) {
       cnt[f] = 0;
       minkey[f] = 0;
       tg[f] = 0;
@@ -214,13 +231,13 @@ exact_scan_kernel(const T* __restrict__ x, int64_t N, int ld, const float* __res
     for (int64_t r = gw; r < N; r += W, ++it) {
       if ((it & 15) == 0) {
 #pragma unroll
-        for (int f = 0; f < kExactF; ++f)
+        for (int f = 0; f < F; ++f)
           if (f < nf) tg[f] = *((volatile unsigned long long*)&tau_g[g0 + f]);
       }
-      float sc[kExactF];
-      warp_exact_scores<T, METRIC, kExactF>(x + r * (int64_t)ld, qs, ld, ld, lane, sc);
+      float sc[F];
+      warp_exact_scores<T, METRIC, F>(x + r * (int64_t)ld, qs, ld, ld, lane, sc);
 #pragma unroll
-      for (int f = 0; f < kExactF; ++f) {
+      for (int f = 0; f < F; ++f) {
         if (f < nf) {
           float s = (METRIC == kMetricIP) ? sc[f] : -sc[f];
           uint64_t key = make_key(s, (uint32_t)r);
@@ -237,7 +254,7 @@ exact_scan_kernel(const T* __restrict__ x, int64_t N, int ld, const float* __res
       }
     }
 #pragma unroll
-    for (int f = 0; f < kExactF; ++f)
+    for (int f = 0; f < F; ++f)
       if (f < nf && lane == 0) cnts[(int64_t)(g0 + f) * W + gw] = cnt[f];
   }
 }

@@ -455,33 +455,28 @@ static int launch_exact(hr_index* h, const int* qsel_dev, int nsel, int k, float
   HR_TRY(h->ex_lists.ensure((size_t)fsel * W * k * 8));
   HR_TRY(h->ex_cnts.ensure((size_t)fsel * W * 4));
   HR_TRY(h->ex_tau.ensure((size_t)fsel * 8));
-  const size_t smem = (size_t)kExactF * h->ld * 4;
-  if (smem > 200 * 1024) return set_err(HR_ERR_INVALID, "d too large for the exact scan kernel");
+  if (smem_q > 200 * 1024) return set_err(HR_ERR_INVALID, "d too large for the exact scan kernel");
+  auto run = [&](auto scan, auto merge, int F, const int* qs, int ns) -> int {
+    const size_t smem = (size_t)F * h->ld * 4;
+    HR_CUDA(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan<<<grid, 256, smem, st>>>((const T*)h->x, h->ntotal, h->ld, h->qpad.as<float>(), qs, ns, k,
+                                  h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>());
+    HR_LAUNCHED();
+    merge<<<ns, 256, 0, st>>>(h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>(), qs, W,
+                              k, h->id_base, D, I);
+    HR_LAUNCHED();
+    return HR_OK;
+  };
   for (int g0 = 0; g0 < nsel; g0 += fsel) {
     const int ns = std::min(fsel, nsel - g0);
     HR_CUDA(cudaMemsetAsync(h->ex_tau.p, 0, (size_t)ns * 8, st));
+    const bool few = ns <= 2;
     if (h->metric == HR_METRIC_INNER_PRODUCT) {
-      HR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<T, kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-      exact_scan_kernel<T, kMetricIP><<<grid, 256, smem, st>>>(
-          (const T*)h->x, h->ntotal, h->ld, h->qpad.as<float>(), qsel_dev + g0, ns, k, h->ex_lists.as<uint64_t>(),
-          h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>());
-      HR_LAUNCHED();
-      exact_merge_kernel<kMetricIP><<<ns, 256, 0, st>>>(h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(),
-                                                        h->ex_tau.as<unsigned long long>(), qsel_dev + g0, W, k,
-                                                        h->id_base, D, I);
-      HR_LAUNCHED();
+      if (few) HR_TRY(run(exact_scan_kernel<T, kMetricIP, 2>, exact_merge_kernel<kMetricIP>, 2, qsel_dev + g0, ns));
+      else HR_TRY(run(exact_scan_kernel<T, kMetricIP, kExactF>, exact_merge_kernel<kMetricIP>, kExactF, qsel_dev + g0, ns));
     } else {
-      HR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<T, kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-      exact_scan_kernel<T, kMetricL2><<<grid, 256, smem, st>>>(
-          (const T*)h->x, h->ntotal, h->ld, h->qpad.as<float>(), qsel_dev + g0, ns, k, h->ex_lists.as<uint64_t>(),
-          h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>());
-      HR_LAUNCHED();
-      exact_merge_kernel<kMetricL2><<<ns, 256, 0, st>>>(h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(),
-                                                        h->ex_tau.as<unsigned long long>(), qsel_dev + g0, W, k,
-                                                        h->id_base, D, I);
-      HR_LAUNCHED();
+      if (few) HR_TRY(run(exact_scan_kernel<T, kMetricL2, 2>, exact_merge_kernel<kMetricL2>, 2, qsel_dev + g0, ns));
+      else HR_TRY(run(exact_scan_kernel<T, kMetricL2, kExactF>, exact_merge_kernel<kMetricL2>, kExactF, qsel_dev + g0, ns));
     }
   }
   return HR_OK;
