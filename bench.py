@@ -344,7 +344,7 @@ def run_b200(args):
     # exact default workload (profiles/r1_scan_bm25_ncu_full.md); other workloads: not captured
     traffic = None
     if (world, args.rows, args.dim, args.nq, args.storage) == (1, 10_000_000, 1024, 1024, "f32+bf16"):
-        traffic = 20.798e9 + 0.083e9
+        traffic = 20.791e9 + 0.039e9
     roofline = {"kernel": kname, "bound": bound, "achieved": achieved, "peak": peak, "unit": runit,
                 "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1_scan_bm25_ncu_full.md)",
                 "peak_source": pk["src"],
