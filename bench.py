@@ -56,7 +56,8 @@ def parse():
                     help="ip: IndexFlatIP (BASELINE.json); l2: IndexFlatL2, what the reference builds "
                          "(rag/storage/faiss_index.py:123); same ranking on unit-norm rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also print an nq sweep of the dense scan (stderr)")
+    ap.add_argument("--sweep", action="store_true", help="(kept for compatibility: the nq sweep is part of the line)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the nq sweep of the dense scan")
     return ap.parse_args()
 
 
@@ -367,8 +368,13 @@ def run_b200(args):
             "second_stage_rescore_queries_in_timed_region": int(flagged[1]), "parity_check": check}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(args, steps=1, warmup=1)
-    if args.sweep and world == 1:
-        for nq in (1, 8, 32, 64, 128, 256, 512, 1024):
+    if world == 1 and not args.no_sweep:
+        # the HBM-bound regime of the same scan kernel family: top-10 dense search for growing batches (scan kernel
+        # time from the library's CUDA events; bytes = the rows the filter streams, once per batch)
+        sweep = {}
+        for nq in (1, 8, 32, 128, 256, 512, 1024):
+            if nq > args.nq:
+                break
             qq = q_dev[:nq].contiguous()
             for _ in range(2):
                 ix.search(qq, 10)
@@ -377,8 +383,12 @@ def run_b200(args):
                 ix.search(qq, 10)
                 ms.append(ix.stats()["scan_ms"])
             m = float(np.median(ms))
+            sweep[str(nq)] = {"scan_ms": m, "hbm_gbs_algorithmic": corpus_bytes / m / 1e6,
+                              "hbm_frac": corpus_bytes / m / 1e6 / pk["hbm_gbs"],
+                              "tflops": 2.0 * nq * n_local * args.dim / m / 1e9}
             log(f"[sweep] nq={nq:5d} scan {m:8.3f} ms  algorithmic HBM {corpus_bytes / m / 1e6:8.1f} GB/s "
                 f"({corpus_bytes / m / 1e6 / pk['hbm_gbs']:.3f} of peak)  {2.0 * nq * n_local * args.dim / m / 1e9:8.1f} TFLOP/s")
+        line["roofline"]["nq_sweep_dense_top10"] = sweep
     print(json.dumps(line), file=_json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
