@@ -358,11 +358,12 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
                         const unsigned int* __restrict__ max_norm2_ord, int64_t id_base, float* __restrict__ D,
                         int64_t* __restrict__ I, int* __restrict__ flagged, int* __restrict__ nflag,
                         const int* __restrict__ qsel, const int* __restrict__ short_tot, int* __restrict__ deeper,
-                        int* __restrict__ ndeeper) {
+                        int* __restrict__ ndeeper, const float* __restrict__ short_s) {
   extern __shared__ uint64_t skeys[];  // [KL]
   __shared__ float s_qn2, s_dq2, s_qt2;
   __shared__ float s_ek;
   __shared__ int s_have_k;
+  __shared__ int s_need;
   const int q = qsel ? qsel[blockIdx.x] : blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -388,7 +389,28 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
       s_qt2 = qt;
     }
   }
-  for (int i = warp; i < n; i += nwarp) {
+  __syncthreads();
+  // the filter's error bound (see the certificate below)
+  const float xn = sqrtf(ord2f(max_norm2_ord[0]));
+  const float dxn = sqrtf(fmaxf(ord2f(max_norm2_ord[1]), 0.f));
+  const float eps = 1.0001f * (sqrtf(s_dq2) * xn + sqrtf(s_qt2) * dxn) + c_acc * sqrtf(s_qn2) * xn +
+                    1e-6f * (s_qn2 + xn * xn) + 1e-30f;
+  // Only rows whose filter score is within 2*eps of the k-th filter score can be in the exact top k: the k rows
+  // in front have exact scores >= s_k - eps, a row behind s_k - 2*eps has an exact score < s_k - eps.  The
+  // candidates are sorted by filter score, so those rows are a prefix.
+  if (threadIdx.x == 0) s_need = n;
+  __syncthreads();
+  if (n > k && short_s) {
+    const float* ss = short_s + (int64_t)q * row_stride;
+    const float cut = ss[k - 1] - 2.f * eps;
+    for (int i = k + threadIdx.x; i < n; i += blockDim.x)
+      if (ss[i] < cut && ss[i - 1] >= cut) s_need = i;   // sorted descending: exactly one boundary (or none)
+    __syncthreads();
+  }
+  const int n_all = n;
+  (void)n_all;
+  const int nn = s_need;
+  for (int i = warp; i < nn; i += nwarp) {
     uint32_t row = short_rows[(int64_t)q * row_stride + i];
     float sc[1];
     warp_exact_scores<T, METRIC, 1>(x + (int64_t)row * ld, qv, ld, ld, lane, sc);
@@ -398,10 +420,10 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
   float* Dq = D + (int64_t)q * k;
   int64_t* Iq = I + (int64_t)q * k;
   const float pad = (METRIC == kMetricIP) ? HR_NEG_INF : -HR_NEG_INF;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
     uint64_t me = skeys[i];
     int rank = 0;
-    for (int j = 0; j < n; ++j) rank += (skeys[j] > me);
+    for (int j = 0; j < nn; ++j) rank += (skeys[j] > me);
     if (rank < k) {
       float s = key_score(me);
       Dq[rank] = (METRIC == kMetricIP) ? s : -s;
@@ -412,7 +434,7 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
       }
     }
   }
-  for (int j = n + threadIdx.x; j < k; j += blockDim.x) {
+  for (int j = nn + threadIdx.x; j < k; j += blockDim.x) {
     Dq[j] = pad;
     Iq[j] = -1;
   }
@@ -425,13 +447,8 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
     } else if (!s_have_k) {
       ok = false;  // rows were dropped but fewer than k survived: cannot certify
     } else {
-      // |q.x - q~.x~| = |dq.x + q~.dx| <= |dq| max|x| + |q~| max|dx| (Cauchy-Schwarz; dq, dx are the operands'
+      // eps: |q.x - q~.x~| = |dq.x + q~.dx| <= |dq| max|x| + |q~| max|dx| (Cauchy-Schwarz; dq, dx are the operands'
       // actual rounding residuals, measured, not their worst case), plus the fp32 accumulation of d terms
-      const float xn = sqrtf(ord2f(max_norm2_ord[0]));
-      const float dxn = sqrtf(fmaxf(ord2f(max_norm2_ord[1]), 0.f));
-      const float qn = sqrtf(s_qn2);
-      float eps = 1.0001f * (sqrtf(s_dq2) * xn + sqrtf(s_qt2) * dxn) + c_acc * qn * xn + 1e-6f * (s_qn2 + xn * xn) +
-                  1e-30f;
       // map the exact k-th best into the filter's score domain
       float shat = (METRIC == kMetricIP) ? s_ek : 0.5f * (s_qn2 + s_ek);  // s_ek = -dist for L2
       ok = shat > tp + eps;

@@ -525,7 +525,7 @@ scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
                   const unsigned int* __restrict__ tau_g, int G, int nq, int KL,
                   uint32_t* __restrict__ short_rows, int* __restrict__ short_n, float* __restrict__ tprime,
                   int* __restrict__ overflow_count, unsigned int* __restrict__ tau_seed,
-                  int* __restrict__ short_tot, float* __restrict__ tprime_tot) {
+                  int* __restrict__ short_tot, float* __restrict__ tprime_tot, float* __restrict__ short_s) {
   __shared__ uint64_t buf[kShortCap];
   __shared__ int s_n;
   __shared__ int hist[256];
@@ -592,7 +592,10 @@ scan_merge_kernel(const Cand* __restrict__ lists, const int* __restrict__ cnts,
   while (pw < n) pw <<= 1;
   for (int i = n + threadIdx.x; i < pw; i += blockDim.x) buf[i] = 0;
   block_bitonic_desc(buf, pw);
-  for (int j = threadIdx.x; j < max(KL, n); j += blockDim.x) out[j] = (j < n) ? key_row(buf[j]) : 0xFFFFFFFFu;
+  for (int j = threadIdx.x; j < max(KL, n); j += blockDim.x) {
+    out[j] = (j < n) ? key_row(buf[j]) : 0xFFFFFFFFu;
+    if (j < n) short_s[(size_t)q * kShortCap + j] = key_score(buf[j]);   // filter scores, best first
+  }
   if (threadIdx.x == 0) {
     short_n[q] = n < KL ? n : KL;
     short_tot[q] = n;

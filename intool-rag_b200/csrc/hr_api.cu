@@ -176,8 +176,8 @@ struct hr_index {
   __nv_bfloat16* xs = nullptr;  // F32_SHADOW16 only: bf16 copy of the rows for the tensor-core filter, [capacity][ld]
   float* norms = nullptr;
   unsigned int* max_norm2 = nullptr;  // ordered-uints: [0] max |x|^2, [1] max |x - filter's view of x|^2
-  DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_n, short_tot, tprime, tprime_tot, flagged, deeper, counters,
-      pre_max;
+  DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_s, short_n, short_tot, tprime, tprime_tot, flagged, deeper,
+      counters, pre_max;
   DevBuf ex_lists, ex_cnts, ex_tau, ex_sel, io_q, io_D, io_I, stage;
   int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow [2]=ndeeper
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -258,7 +258,7 @@ extern "C" int hr_index_destroy(hr_index* h) {
   if (h->max_norm2) cudaFree(h->max_norm2);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   DevBuf* bufs[] = {&h->qpad, &h->qh, &h->lists, &h->cnts, &h->tau_g, &h->short_rows, &h->short_n, &h->tprime,
-                    &h->flagged, &h->counters, &h->pre_max, &h->short_tot, &h->tprime_tot, &h->deeper, &h->ex_lists, &h->ex_cnts, &h->ex_tau, &h->ex_sel, &h->io_q,
+                    &h->flagged, &h->counters, &h->pre_max, &h->short_tot, &h->tprime_tot, &h->deeper, &h->short_s, &h->ex_lists, &h->ex_cnts, &h->ex_tau, &h->ex_sel, &h->io_q,
                     &h->io_D, &h->io_I, &h->stage, &h->rs.q, &h->rs.qi, &h->rs.qt, &h->rs.dD, &h->rs.dI,
                     &h->rs.bS, &h->rs.bI, &h->rs.oS, &h->rs.oI};
   for (DevBuf* b : bufs) b->release();
@@ -520,12 +520,12 @@ static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_acc, float
     rescore_finalize_kernel<T, kMetricIP><<<blocks, 256, smem, st>>>(
         (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), kShortCap, n_in, tp, depth, k, c_acc,
         fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(), h->counters.as<int>(), qsel,
-        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2);
+        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2, h->short_s.as<float>());
   else
     rescore_finalize_kernel<T, kMetricL2><<<blocks, 256, smem, st>>>(
         (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), kShortCap, n_in, tp, depth, k, c_acc,
         fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(), h->counters.as<int>(), qsel,
-        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2);
+        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2, h->short_s.as<float>());
   HR_LAUNCHED();
   return HR_OK;
 }
@@ -584,6 +584,7 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     HR_TRY(h->cnts.ensure((size_t)h->num_sms * nb * 4));
     HR_TRY(h->tau_g.ensure((size_t)nb * 4));
     HR_TRY(h->short_rows.ensure((size_t)nb * kShortCap * 4));
+    HR_TRY(h->short_s.ensure((size_t)nb * kShortCap * 4));
     HR_TRY(h->short_tot.ensure((size_t)nb * 4));
     HR_TRY(h->tprime_tot.ensure((size_t)nb * 4));
     HR_TRY(h->deeper.ensure((size_t)nb * 4));
@@ -666,7 +667,7 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
     scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), gmain,
                                           nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
                                           h->tprime.as<float>(), h->counters.as<int>() + 1, nullptr,
-                                          h->short_tot.as<int>(), h->tprime_tot.as<float>());
+                                          h->short_tot.as<int>(), h->tprime_tot.as<float>(), h->short_s.as<float>());
     HR_LAUNCHED();
     // filter error bound = measured rounding residuals of both operands (rescore_finalize_kernel) + this
     // relative allowance for the fp32 accumulation over ld terms
