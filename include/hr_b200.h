@@ -9,10 +9,11 @@
  * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding.
  *
  * Ownership: the caller owns every input/output buffer; a handle owns its corpus /
- * postings device memory and its scratch.  A handle is bound to one CUDA device; calls on
- * one handle must not overlap (one in-flight search per handle); `add` never runs
- * concurrently with `search` (the reference adds at ingest into a new index,
- * rag/ingest/ingestion_pipeline.py:88).  There is no CPU fallback: without a CUDA device
+ * postings device memory and its scratch.  A handle is bound to one CUDA device.  Calls on
+ * one handle are serialised by a mutex inside the handle (the scratch is per handle), so
+ * concurrent searches from several threads are safe, like faiss-cpu's IndexFlat::search; use
+ * several handles for concurrency.  (The reference adds at ingest into a new index,
+ * rag/ingest/ingestion_pipeline.py:88, and searches from one event-loop thread.)  There is no CPU fallback: without a CUDA device
  * every compute entry point fails with HR_ERR_CUDA.
  */
 #ifndef HR_B200_H
@@ -56,6 +57,7 @@ extern "C" {
 
 typedef struct hr_index hr_index; /* flat dense index                                      */
 typedef struct hr_bm25 hr_bm25;   /* BM25 inverted index (CSR by term)                     */
+typedef struct hr_comm hr_comm;   /* one rank of a row-sharded corpus (NCCL communicator)  */
 
 typedef struct hr_scan_stats {
   int64_t launches;         /* kernels launched by the last search on this handle        */
@@ -75,6 +77,9 @@ int hr_version(void);
 int hr_device_count(int* out);
 /* kernels launched by this library in this process (monotonic; bench.py's gpu_launches). */
 int64_t hr_launch_count(void);
+/* tuning / diagnostic knobs by name = the HR_* environment variables without the prefix, lower case
+ * ("bm25_spans", "bm25_wide", "pre_tiles", ...).  Benchmarks and tests only. */
+int hr_set_option(const char* name, int value);
 
 /* ---- flat dense index: replaces faiss.IndexFlatL2/IP ---------------------------------
  * create  <- faiss.IndexFlatL2(d)            rag/storage/faiss_index.py:123
@@ -145,7 +150,8 @@ int64_t hr_bm25_vocab(const hr_bm25* h);
 int64_t hr_bm25_nnz(const hr_bm25* h);
 int hr_bm25_set_id_base(hr_bm25* h, int64_t id_base);
 /* queries as CSR: q_indptr int32[nq+1], q_terms int32[n_terms] with n_terms >= q_indptr[nq]
- * (duplicates count, ids outside [0,V) ignored, at most 64 terms per query).  n_terms < 0 = unknown
+ * (duplicates count, ids outside [0,V) ignored; any length, but at most 64 DISTINCT scorable terms per
+ * query: more is HR_ERR_INVALID, for host and device queries alike).  n_terms < 0 = unknown
  * (device io then reads q_indptr[nq] back, one small synchronous copy).  S float32[nq,k]
  * descending, I int64[nq,k], padding I=-1,S=0.  postings_touched (optional, host int64)
  * receives the number of postings scored. */
@@ -185,6 +191,24 @@ int hr_merge_fuse_lists(hr_index* ix, const float* D, const int64_t* I, const fl
 int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
                 const int32_t* q_terms, int64_t nq, int64_t n_terms, int top_k, int kc, int mode, float w_vec,
                 float w_bm25, float* out_S, int64_t* out_I, int io_on_device, void* stream);
+
+/* ---- row-sharded corpus, one process per GPU (the reference is single-process) -----------
+ * The corpus is split by row: rank r holds rows [lo_r, hi_r) in `ix` / `bm` (id_base = lo_r, BM25 built with the
+ * corpus-wide n_docs_global / avgdl_global / df_global).  hr_retrieve_sharded = hr_retrieve on every rank's
+ * shard + ONE ncclAllGather of the (world x kc) candidates per query and modality + merge under (score best
+ * first, id asc) + fusion, all enqueued on `stream` by one call; every rank returns the same answer, equal to
+ * hr_retrieve on the unsplit corpus.  NCCL is bound at run time (dlopen "libnccl.so.2", or $HR_NCCL_LIB); a
+ * world of 1 needs no NCCL.  Rank 0 calls hr_comm_unique_id and ships the 128 bytes to the other ranks over
+ * any channel (torch.distributed broadcast, a file, a socket); then every rank calls hr_comm_init.
+ * Collective: every rank must call hr_retrieve_sharded with the same nq, kc, top_k and mode. */
+int hr_comm_unique_id(void* out_id_128_bytes);
+int hr_comm_init(const void* unique_id_128_bytes, int rank, int world, int device, hr_comm** out);
+int hr_comm_destroy(hr_comm* c);
+int hr_comm_rank(const hr_comm* c);
+int hr_comm_world(const hr_comm* c);
+int hr_retrieve_sharded(hr_comm* c, hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
+                        const int32_t* q_terms, int64_t nq, int64_t n_terms, int top_k, int kc, int mode,
+                        float w_vec, float w_bm25, float* out_S, int64_t* out_I, int io_on_device, void* stream);
 
 #ifdef __cplusplus
 }

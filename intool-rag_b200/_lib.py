@@ -35,6 +35,7 @@ SYMBOLS = {
     "hr_version": (C.c_int, []),
     "hr_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "hr_launch_count": (C.c_int64, []),
+    "hr_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "hr_index_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
     "hr_index_destroy": (C.c_int, [_p]),
     "hr_index_reserve": (C.c_int, [_p, C.c_int64]),
@@ -70,6 +71,13 @@ SYMBOLS = {
     "hr_candidates": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int, _p, _p, _p, _p, _p]),
     "hr_merge_fuse_lists": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_float, _p, _p, _p]),
+    "hr_comm_unique_id": (C.c_int, [_p]),
+    "hr_comm_init": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
+    "hr_comm_destroy": (C.c_int, [_p]),
+    "hr_comm_rank": (C.c_int, [_p]),
+    "hr_comm_world": (C.c_int, [_p]),
+    "hr_retrieve_sharded": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, _p, _p, C.c_int, _p]),
     "hr_retrieve": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                               _p, _p, C.c_int, _p]),
 }
@@ -117,6 +125,11 @@ def require_gpu() -> None:
 
 def launch_count() -> int:
     return int(lib().hr_launch_count())
+
+
+def set_option(name: str, value: int) -> None:
+    """Tuning / diagnostic knob of the library (include/hr_b200.h: hr_set_option)."""
+    check(lib().hr_set_option(name.encode(), int(value)))
 
 
 def current_stream_ptr(device: int | None = None) -> int:

@@ -49,6 +49,23 @@ class Vocabulary:
         return len(self.word_to_id)
 
 
+MAX_DISTINCT_TERMS = 64   # per query, what one warp of the scoring kernel owns (include/hr_b200.h: hr_bm25_search)
+
+
+def cap_query_terms(tokens: Sequence[int], max_distinct: int = MAX_DISTINCT_TERMS) -> List[int]:
+    """Service adapter for long query texts: keep every occurrence of the first `max_distinct` distinct term ids
+    (duplicates still count per occurrence), drop the rest.  The library itself rejects a query with more than 64
+    distinct scorable terms (HR_ERR_INVALID) on every input path instead of truncating silently."""
+    seen, out = set(), []
+    for t in tokens:
+        if t not in seen:
+            if len(seen) >= max_distinct:
+                continue
+            seen.add(t)
+        out.append(t)
+    return out
+
+
 def query_csr(queries) -> Tuple[np.ndarray, np.ndarray]:
     """ragged list of int lists -> (indptr int32[nq+1], terms int32[total]); a CSR pair passes through."""
     if isinstance(queries, tuple) and len(queries) == 2:

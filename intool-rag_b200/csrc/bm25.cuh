@@ -2,9 +2,12 @@
 //
 // The reference advertises BM25 (README.md:54-58, rag/config.py:43-45) but implements none; the
 // definition is oracle/bm25.py.  Layout in HBM (struct of arrays):
-//   indptr int64[V+1] | post_doc int32[nnz] (ascending per term) | post_imp fp32[nnz]
-// post_imp is the length-normalised saturation tf(k1+1)/(tf+k1(1-b+b dl/avgdl)) folded at build
-// time, so one posting costs 8 streamed bytes and score(q,d) = sum_t mult(t) idf(t) imp(t,d).
+//   indptr int64[V+1] (list lengths / df) | pstart int64[V+1] | post_doc int32[nnz_pad] | post_imp fp32[nnz_pad]
+// List t occupies [pstart[t], pstart[t] + len_t), doc ids ascending; every list starts at a multiple of 4 and is
+// padded to the next multiple of 4 with sentinels (doc = INT_MAX, impact = 0), so 16-byte groups of postings
+// never straddle two lists (bm25_sweep.cuh).  post_imp is the length-normalised saturation
+// tf(k1+1)/(tf+k1(1-b+b dl/avgdl)) folded at build time, so one posting costs 8 streamed bytes and
+// score(q,d) = sum_t mult(t) idf(t) imp(t,d).
 //
 // A search is three kernels:
 //   bm25_plan_terms_kernel   per query: de-duplicate the terms (first-occurrence order, multiplicity
@@ -35,7 +38,7 @@
 
 namespace hr {
 
-constexpr int kBmMaxTerms = 64;   // raw terms per query
+constexpr int kBmMaxTerms = 64;   // distinct scorable terms per query (lane t owns terms t and t + 32)
 constexpr int kBmMaxK = 128;      // candidate depth the kernel supports
 constexpr int kBsThreads = 256;
 constexpr int kBsWarps = kBsThreads / 32;
@@ -56,15 +59,78 @@ __host__ __device__ constexpr int bs_smem_bytes(int kcp) {
   return kBsWarps * bs_slice_docs(kcp) * 4 + kBsWarps * 2 * kcp * 8;
 }
 
-__global__ void bm25_impact_kernel(const int32_t* __restrict__ post_doc, const int32_t* __restrict__ post_tf,
-                                   const int32_t* __restrict__ doc_len, int64_t nnz, double k1, double b,
-                                   double avgdl, float* __restrict__ imp) {
+constexpr int32_t kBmSentinelDoc = 0x7FFFFFFF;
+
+// CSR (indptr, post_doc, post_tf) -> padded posting arrays with folded impacts.  Thread = posting i: its term
+// by a binary search in indptr, destination pstart[t] + (i - indptr[t]).  Validates what the scoring kernels
+// rely on: 0 <= doc < n_docs, doc ids strictly ascending inside a list, tf > 0 (bad[0] counts violations).
+__global__ void bm25_pad_impact_kernel(const int64_t* __restrict__ indptr, const int64_t* __restrict__ pstart,
+                                       const int32_t* __restrict__ post_doc, const int32_t* __restrict__ post_tf,
+                                       const int32_t* __restrict__ doc_len, int64_t nnz, int64_t vocab,
+                                       int64_t n_docs, double k1, double b, double avgdl,
+                                       int32_t* __restrict__ out_doc, float* __restrict__ out_imp,
+                                       unsigned long long* __restrict__ bad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
-    double tf = (double)post_tf[i];
-    double dl = (double)doc_len[post_doc[i]];
-    double norm = avgdl > 0.0 ? k1 * (1.0 - b + b * dl / avgdl) : k1;
-    imp[i] = (float)(tf * (k1 + 1.0) / (tf + norm));
+    int64_t lo = 0, hi = vocab;   // last t with indptr[t] <= i
+    while (lo < hi) {
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (__ldg(indptr + mid) <= i) lo = mid; else hi = mid - 1;
+    }
+    const int64_t t0 = __ldg(indptr + lo);
+    const int32_t doc = post_doc[i];
+    const int32_t tfi = post_tf[i];
+    bool ok = doc >= 0 && (int64_t)doc < n_docs && tfi > 0;
+    if (ok && i > t0) ok = post_doc[i - 1] < doc;
+    if (!ok) {
+      atomicAdd(bad, 1ull);
+      continue;
+    }
+    const double tf = (double)tfi;
+    const double dl = (double)doc_len[doc];
+    const double norm = avgdl > 0.0 ? k1 * (1.0 - b + b * dl / avgdl) : k1;
+    const int64_t dst = __ldg(pstart + lo) + (i - t0);
+    out_doc[dst] = doc;
+    out_imp[dst] = (float)(tf * (k1 + 1.0) / (tf + norm));
+  }
+}
+
+// sentinels behind every list (up to the next multiple of 4) and behind the last one
+__global__ void bm25_pad_sentinels_kernel(const int64_t* __restrict__ indptr, const int64_t* __restrict__ pstart,
+                                          int64_t vocab, int64_t tail, int32_t* __restrict__ out_doc,
+                                          float* __restrict__ out_imp) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; t < vocab; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = pstart[t] + (indptr[t + 1] - indptr[t]);
+    for (int64_t j = e; j < pstart[t + 1]; ++j) {
+      out_doc[j] = kBmSentinelDoc;
+      out_imp[j] = 0.f;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < tail) {
+    out_doc[pstart[vocab] + threadIdx.x] = kBmSentinelDoc;
+    out_imp[pstart[vocab] + threadIdx.x] = 0.f;
+  }
+}
+
+// load-time validation of a padded index read from a file: lists ascending, docs in range, padding = sentinels
+__global__ void bm25_check_padded_kernel(const int64_t* __restrict__ indptr, const int64_t* __restrict__ pstart,
+                                         const int32_t* __restrict__ post_doc, int64_t vocab, int64_t n_docs,
+                                         unsigned long long* __restrict__ bad) {
+  // a warp per term, lanes over its padded list
+  const int lane = threadIdx.x & 31;
+  int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; t < vocab; t += nw) {
+    const int64_t p0 = pstart[t], len = indptr[t + 1] - indptr[t], pe = pstart[t + 1];
+    unsigned long long nb = 0;
+    for (int64_t j = p0 + lane; j < pe; j += 32) {
+      const int32_t d = post_doc[j];
+      if (j < p0 + len) {
+        if (d < 0 || (int64_t)d >= n_docs || (j > p0 && post_doc[j - 1] >= d)) nb++;
+      } else if (d != kBmSentinelDoc) nb++;
+    }
+    if (nb) atomicAdd(bad, nb);
   }
 }
 
@@ -92,15 +158,17 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t* keys, int n, int lan
 // One warp per query.  Slot u of query q lives at index q_indptr[q] + u of the plan arrays (u < nt[q] <=
 // raw term count), in order of first occurrence.
 __global__ void __launch_bounds__(256)
-bm25_plan_terms_kernel(const int64_t* __restrict__ indptr, const float* __restrict__ idf, int64_t V,
+bm25_plan_terms_kernel(const int64_t* __restrict__ indptr, const int64_t* __restrict__ pstart,
+                       const float* __restrict__ idf, int64_t V,
                        const int32_t* __restrict__ q_indptr, const int32_t* __restrict__ q_terms, int nq,
                        int* __restrict__ plan_nt, int64_t* __restrict__ plan_start, uint32_t* __restrict__ plan_len,
-                       float* __restrict__ plan_wgt, unsigned long long* __restrict__ postings_touched) {
+                       float* __restrict__ plan_wgt, unsigned long long* __restrict__ postings_touched,
+                       int* __restrict__ too_many) {
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
   const int qa = q_indptr[q];
-  const int nraw = min(q_indptr[q + 1] - qa, kBmMaxTerms);
+  const int nraw = q_indptr[q + 1] - qa;   // any length; at most kBmMaxTerms DISTINCT scorable terms
   int base = 0;
   unsigned long long touched = 0;
   for (int r0 = 0; r0 < nraw; r0 += 32) {
@@ -112,11 +180,13 @@ bm25_plan_terms_kernel(const int64_t* __restrict__ indptr, const float* __restri
     if (i < nraw) {
       t = q_terms[qa + i];
       keep = (t >= 0 && t < V);
-      for (int j = 0; j < nraw; ++j) {
-        const int u = q_terms[qa + j];
-        if (u == t) {
-          if (j < i) keep = false;
-          mult++;
+      if (keep) {
+        for (int j = 0; j < nraw; ++j) {
+          const int u = q_terms[qa + j];
+          if (u == t) {
+            if (j < i) keep = false;
+            mult++;
+          }
         }
       }
       if (keep) {
@@ -125,10 +195,16 @@ bm25_plan_terms_kernel(const int64_t* __restrict__ indptr, const float* __restri
         keep = e > a;
       }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (base + __popc(m) > kBmMaxTerms) {
+      // more distinct terms than a warp owns: report (the host turns it into HR_ERR_INVALID), keep the first 64
+      if (lane == 0 && too_many) atomicAdd(too_many, 1);
+      keep = keep && (base + __popc(m & ((1u << lane) - 1u)) < kBmMaxTerms);
+      m = __ballot_sync(0xffffffffu, keep);
+    }
     if (keep) {
       const int slot = qa + base + __popc(m & ((1u << lane) - 1u));
-      plan_start[slot] = a;
+      plan_start[slot] = pstart[t];
       plan_len[slot] = (uint32_t)(e - a);
       plan_wgt[slot] = (float)mult * idf[t];
       touched += (unsigned long long)(e - a);

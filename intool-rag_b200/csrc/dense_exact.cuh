@@ -202,8 +202,16 @@ template <typename T, int METRIC, int F>
 __global__ void __launch_bounds__(256)
 exact_scan_kernel(const T* __restrict__ x, int64_t N, int ld, const float* __restrict__ qpad,
                   const int* __restrict__ qsel, int nsel, int k, uint64_t* __restrict__ lists,
-                  int* __restrict__ cnts, unsigned long long* __restrict__ tau_g) {
+                  int* __restrict__ cnts, unsigned long long* __restrict__ tau_g,
+                  const int* __restrict__ nsel_dev, int nsel_lo, int nsel_hi) {
   extern __shared__ __align__(16) float qs[];  // [F][ld]
+  // device-driven launch (the certificate's fallback, enqueued without a host round-trip): the number of
+  // selected queries is read here; the kernel runs only when it lies in [nsel_lo, nsel_hi] (nsel = capacity)
+  if (nsel_dev) {
+    const int nd = *nsel_dev;
+    if (nd < nsel_lo || nd > nsel_hi) return;
+    nsel = min(nd, nsel);
+  }
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -266,11 +274,13 @@ template <int METRIC>
 __global__ void __launch_bounds__(256)
 exact_merge_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ cnts,
                    const unsigned long long* __restrict__ tau_g, const int* __restrict__ qsel, int64_t W, int k,
-                   int64_t id_base, float* __restrict__ D, int64_t* __restrict__ I) {
+                   int64_t id_base, float* __restrict__ D, int64_t* __restrict__ I,
+                   const int* __restrict__ nsel_dev) {
   __shared__ uint64_t buf[kMergeCap];
   __shared__ int s_n;
   __shared__ unsigned long long s_best;
   const int f = blockIdx.x;
+  if (nsel_dev && f >= *nsel_dev) return;   // device-driven launch with the capacity as grid
   const int q = qsel[f];
   const uint64_t thr = tau_g[f];
   if (threadIdx.x == 0) s_n = 0;
@@ -358,8 +368,10 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
                         const unsigned int* __restrict__ max_norm2_ord, int64_t id_base, float* __restrict__ D,
                         int64_t* __restrict__ I, int* __restrict__ flagged, int* __restrict__ nflag,
                         const int* __restrict__ qsel, const int* __restrict__ short_tot, int* __restrict__ deeper,
-                        int* __restrict__ ndeeper, const float* __restrict__ short_s) {
+                        int* __restrict__ ndeeper, const float* __restrict__ short_s,
+                        const int* __restrict__ nsel_dev) {
   extern __shared__ uint64_t skeys[];  // [KL]
+  if (nsel_dev && (int)blockIdx.x >= *nsel_dev) return;   // stage 2 is launched for every query, runs for the listed ones
   __shared__ float s_qn2, s_dq2, s_qt2;
   __shared__ float s_ek;
   __shared__ int s_have_k;

@@ -15,6 +15,11 @@ constexpr int kFuseMaxKc = 256;
 __device__ __forceinline__ bool ranks_before(float sa, int64_t ia, float sb, int64_t ib) {
   return (sa > sb) || (sa == sb && ia < ib);
 }
+// total order for rank-by-counting: entries with an equal (score, id) — duplicate ids from overlapping shards —
+// are ordered by their position, so the ranks are a permutation and every output slot is written
+__device__ __forceinline__ bool ranks_before_pos(float sa, int64_t ia, int pa, float sb, int64_t ib, int pb) {
+  return (sa > sb) || (sa == sb && (ia < ib || (ia == ib && pa < pb)));
+}
 
 // One block per query.  Entries [0,kc) = dense list, [kc,2kc) = sparse list (only sparse-only docs valid).
 __global__ void __launch_bounds__(256)
@@ -79,7 +84,7 @@ fuse_kernel(const float* __restrict__ dD, const int64_t* __restrict__ dI, const 
     int rank = 0;
     for (int j = 0; j < n2; ++j) {
       const int64_t oj = fid[j];
-      if (oj >= 0 && ranks_before(fs[j], oj, f, id)) rank++;
+      if (oj >= 0 && ranks_before_pos(fs[j], oj, j, f, id, e)) rank++;
     }
     if (rank < top_k) {
       oS[(size_t)q * top_k + rank] = f;
@@ -111,6 +116,7 @@ merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, in
     const int l = e / kc, c = e - l * kc;
     float s = S[(size_t)l * s_stride + (size_t)q * kc + c];
     int64_t id = I[(size_t)l * i_stride + (size_t)q * kc + c];
+    if (s != s) s = pad_score;   // NaN has no place in a total order: it ranks like padding
     ss[e] = largest ? s : -s;
     si[e] = id;
     if (id >= 0) atomicAdd(&s_valid, 1);
@@ -124,7 +130,7 @@ merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, in
     int rank = 0;
     for (int j = 0; j < n_cand; ++j) {
       const int64_t oj = si[j];
-      if (oj >= 0 && ranks_before(ss[j], oj, f, id)) rank++;
+      if (oj >= 0 && ranks_before_pos(ss[j], oj, j, f, id, e)) rank++;
     }
     if (rank < k) {
       oS[(size_t)q * k + rank] = largest ? f : -f;

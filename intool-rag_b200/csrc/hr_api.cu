@@ -3,6 +3,7 @@
 // There is NO CPU compute path in this file: without a CUDA device every entry point fails.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -10,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,6 +20,7 @@
 #include "dense_exact.cuh"
 #include "dense_scan_tc.cuh"
 #include "bm25.cuh"
+#include "bm25_sweep.cuh"
 #include "bm25_build.cuh"
 #include "fuse.cuh"
 
@@ -61,9 +64,13 @@ struct Tuning {
   int pre_rank = 2;     // HR_PRE_RANK: target corpus rank of the seeded threshold, in units of KL
   int bm25_waves = 8;   // HR_BM25_WAVES: BM25 CTAs per resident slot
   bool no_pair = false; // HR_NO_PAIR: never use the cta_group::2 scan kernel
+  int bm25_impl = 0;    // HR_BM25_IMPL: 0 = flat-sweep kernel (bm25_sweep.cuh), 1 = round-1 slot kernel (bm25.cuh)
+  int bm25_wide = 0;    // HR_BM25_WIDE: 1 = one CTA per SM with twice the slice (6144 docs) instead of two CTAs
+  int bm25_spans = 0;   // HR_BM25_SPANS: doc windows per query (0 = automatic)
+  int bm25_batch = 3;   // HR_BM25_BATCH: 3 = deeper load batch (3 iterations in flight; 4 on the wide variant), 2 = one less
 };
-static const Tuning& tuning() {
-  static const Tuning t = [] {
+static Tuning& tuning_mut() {
+  static Tuning t = [] {
     Tuning x;
     auto geti = [](const char* name, int dflt, int lo, int hi) {
       const char* v = getenv(name);
@@ -76,10 +83,15 @@ static const Tuning& tuning() {
     x.pre_rank = geti("HR_PRE_RANK", x.pre_rank, 1, 16);
     x.bm25_waves = geti("HR_BM25_WAVES", x.bm25_waves, 1, 64);
     x.no_pair = getenv("HR_NO_PAIR") != nullptr;
+    x.bm25_impl = geti("HR_BM25_IMPL", 0, 0, 1);
+    x.bm25_wide = geti("HR_BM25_WIDE", 0, 0, 1);
+    x.bm25_spans = geti("HR_BM25_SPANS", 0, 0, 65535);
+    x.bm25_batch = geti("HR_BM25_BATCH", 3, 2, 3);
     return x;
   }();
   return t;
 }
+static const Tuning& tuning() { return tuning_mut(); }
 
 struct DeviceGuard {
   int prev = -1;
@@ -182,6 +194,13 @@ struct hr_index {
   int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow [2]=ndeeper
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   hr_scan_stats stats{};
+  // a chunk whose device-side counters have not been read back yet (chunk_enqueue / chunk_finish)
+  bool pend = false;
+  int pend_cap = 0, pend_k = 0;
+  float* pend_D = nullptr;
+  int64_t* pend_I = nullptr;
+  long long launches0 = 0;
+  std::mutex mu;   // one search / add at a time per handle: the scratch above is per handle
 };
 
 static size_t row_bytes(const hr_index* h) { return (size_t)h->ld * h->elem; }
@@ -193,6 +212,25 @@ static int filter_elem(const hr_index* h) { return filter_is_bf16(h) ? 2 : 4; }
 extern "C" const char* hr_last_error(void) { return g_err.c_str(); }
 extern "C" int hr_version(void) { return 100; }
 extern "C" int64_t hr_launch_count(void) { return (int64_t)g_launches.load(); }
+// Tuning / diagnostic knobs by name (the HR_* environment variables without the prefix, lower case).  Not
+// thread-safe against running searches; meant for benchmarks and tests.
+extern "C" int hr_set_option(const char* name, int value) {
+  if (!name) return set_err(HR_ERR_INVALID, "null option name");
+  Tuning& t = tuning_mut();
+  const std::string n(name);
+  auto clamp = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  if (n == "qrows") t.q_rows = clamp(value, 1, 128);
+  else if (n == "pre_tiles") t.pre_tiles = clamp(value, 1, 64);
+  else if (n == "pre_rank") t.pre_rank = clamp(value, 1, 16);
+  else if (n == "bm25_waves") t.bm25_waves = clamp(value, 1, 64);
+  else if (n == "no_pair") t.no_pair = value != 0;
+  else if (n == "bm25_impl") t.bm25_impl = clamp(value, 0, 1);
+  else if (n == "bm25_wide") t.bm25_wide = clamp(value, 0, 1);
+  else if (n == "bm25_spans") t.bm25_spans = clamp(value, 0, 65535);
+  else if (n == "bm25_batch") t.bm25_batch = clamp(value, 2, 3);
+  else return set_err(HR_ERR_INVALID, "unknown option: " + n);
+  return HR_OK;
+}
 extern "C" int hr_device_count(int* out) {
   if (!out) return set_err(HR_ERR_INVALID, "null out");
   int n = 0;
@@ -209,7 +247,8 @@ extern "C" int hr_device_count(int* out) {
 extern "C" int hr_index_create(int d, int metric, int storage_dtype, int device, hr_index** out) {
   if (!out) return set_err(HR_ERR_INVALID, "null out");
   *out = nullptr;
-  if (d <= 0 || d > 65536) return set_err(HR_ERR_INVALID, "d must be in [1, 65536]");
+  // the exact re-score / fallback kernels keep kExactF padded query rows in shared memory (200 KB): d <= 6400
+  if (d <= 0 || d > 6400) return set_err(HR_ERR_INVALID, "d must be in [1, 6400]");
   if (metric != HR_METRIC_INNER_PRODUCT && metric != HR_METRIC_L2)
     return set_err(HR_ERR_INVALID, "metric must be METRIC_INNER_PRODUCT (0) or METRIC_L2 (1)");
   if (storage_dtype != HR_STORAGE_F32 && storage_dtype != HR_STORAGE_BF16 && storage_dtype != HR_STORAGE_F32_SHADOW16)
@@ -244,7 +283,12 @@ extern "C" int hr_index_create(int d, int metric, int storage_dtype, int device,
     delete h;
     return set_err(HR_ERR_NOMEM, "allocation failed in hr_index_create");
   }
-  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 4; ++i)
+    if (cudaEventCreate(&h->ev[i]) != cudaSuccess) {
+      (void)cudaGetLastError();
+      hr_index_destroy(h);
+      return set_err(HR_ERR_CUDA, "cudaEventCreate failed in hr_index_create");
+    }
   *out = h;
   return HR_OK;
 }
@@ -281,13 +325,21 @@ static int index_grow(hr_index* h, int64_t need, cudaStream_t st) {
     (void)cudaGetLastError();
     if (nx) cudaFree(nx);
     if (nn) cudaFree(nn);
+    if (ns) cudaFree(ns);
     return set_err(HR_ERR_NOMEM, "cudaMalloc failed while growing the index (corpus does not fit in HBM?)");
   }
   if (h->ntotal > 0) {
-    HR_CUDA(cudaMemcpyAsync(nx, h->x, (size_t)h->ntotal * row_bytes(h), cudaMemcpyDeviceToDevice, st));
-    HR_CUDA(cudaMemcpyAsync(nn, h->norms, (size_t)h->ntotal * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (shadow) HR_CUDA(cudaMemcpyAsync(ns, h->xs, (size_t)h->ntotal * h->ld * 2, cudaMemcpyDeviceToDevice, st));
-    HR_CUDA(cudaStreamSynchronize(st));
+    cudaError_t c = cudaMemcpyAsync(nx, h->x, (size_t)h->ntotal * row_bytes(h), cudaMemcpyDeviceToDevice, st);
+    if (c == cudaSuccess) c = cudaMemcpyAsync(nn, h->norms, (size_t)h->ntotal * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (c == cudaSuccess && shadow) c = cudaMemcpyAsync(ns, h->xs, (size_t)h->ntotal * h->ld * 2, cudaMemcpyDeviceToDevice, st);
+    if (c == cudaSuccess) c = cudaStreamSynchronize(st);
+    if (c != cudaSuccess) {
+      (void)cudaGetLastError();
+      cudaFree(nx);
+      cudaFree(nn);
+      if (ns) cudaFree(ns);
+      return set_err(HR_ERR_CUDA, std::string("copy failed while growing the index: ") + cudaGetErrorString(c));
+    }
   }
   if (h->x) cudaFree(h->x);
   if (h->xs) cudaFree(h->xs);
@@ -303,6 +355,7 @@ extern "C" int hr_index_reserve(hr_index* h, int64_t n_rows) {
   if (!h) return set_err(HR_ERR_INVALID, "null index");
   if (n_rows < 0 || n_rows >= (int64_t)0xFFFFFFF0ll) return set_err(HR_ERR_INVALID, "n_rows out of range");
   HR_DEVICE(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
   return index_grow(h, n_rows, 0);
 }
 
@@ -313,6 +366,7 @@ extern "C" int hr_index_add(hr_index* h, const float* x, int64_t n, int is_devic
   if (!x) return set_err(HR_ERR_INVALID, "null x");
   if (h->ntotal + n >= (int64_t)0xFFFFFFF0ll) return set_err(HR_ERR_INVALID, "too many rows for one shard");
   HR_DEVICE(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
   cudaStream_t st = (cudaStream_t)stream;
   if (h->ntotal + n > h->capacity) {
     int64_t want = h->ntotal + n;
@@ -354,6 +408,7 @@ extern "C" int hr_index_add(hr_index* h, const float* x, int64_t n, int is_devic
 extern "C" int hr_index_reset(hr_index* h) {
   if (!h) return set_err(HR_ERR_INVALID, "null index");
   HR_DEVICE(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
   h->ntotal = 0;
   HR_CUDA(cudaMemset(h->max_norm2, 0, 2 * sizeof(unsigned int)));
   return HR_OK;
@@ -383,6 +438,7 @@ extern "C" int hr_index_debug_dump(hr_index* h, int64_t nq, void* lists, int32_t
                                    uint32_t* short_rows, float* tprime) {
   if (!h) return set_err(HR_ERR_INVALID, "null index");
   HR_DEVICE(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
   const int64_t G = h->stats.grid, KL = h->stats.list_len;
   if (h->stats.mode_used != HR_MODE_AUTO || G <= 0 || nq <= 0 || nq > kScanNqMax)
     return set_err(HR_ERR_INVALID, "debug_dump: last search did not run the filter scan");
@@ -402,6 +458,7 @@ extern "C" int hr_index_reconstruct(hr_index* h, int64_t i0, int64_t n, float* o
   if (i0 < 0 || n < 0 || i0 + n > h->ntotal) return set_err(HR_ERR_INVALID, "reconstruct: row range out of bounds");
   if (n == 0) return HR_OK;
   HR_DEVICE(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
   const int64_t chunk = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->d * 4));
   for (int64_t r0 = 0; r0 < n; r0 += chunk) {
     const int64_t nr = std::min(chunk, n - r0);
@@ -440,9 +497,19 @@ static int list_len_for_k(int k) {
   return 256;
 }
 
+// queries the device-driven fallback (enqueued without knowing the count) handles per chunk; more than that
+// (pathological ties) are finished on the host-driven path after the caller's synchronisation
+constexpr int kExactDevCap = 64;
+
+static int exact_group(int k) { return std::max(kExactF, std::min(kExactDevCap, (64 * 128 / std::max(k, 1)) / kExactF * kExactF)); }
+
+// Exhaustive exact scan of the queries listed in qsel_dev (device), results written to D/I rows qsel[i].
+// Host-driven (nsel_dev == nullptr): nsel queries, in groups.  Device-driven: the count is read on the device
+// from *nsel_dev (at most `nsel` = capacity are handled); both kernel variants are launched and exit at once
+// unless the count is in their range, so nothing here waits for the host.
 template <typename T>
-static int launch_exact(hr_index* h, const int* qsel_dev, int nsel, int k, float* D, int64_t* I, cudaStream_t st) {
-  // exhaustive exact scan of the queries listed in qsel_dev (device), results written to D/I rows qsel[i]
+static int launch_exact(hr_index* h, const int* qsel_dev, int nsel, int k, float* D, int64_t* I, cudaStream_t st,
+                        const int* nsel_dev = nullptr) {
   // warps in flight set the memory-level parallelism of this row-per-warp scan: as many CTAs per SM as the
   // query tile in shared memory allows, up to 2 (measured at 10M x 1024: 39 / 28 / 35 ms per 8 queries with 1 / 2 / 4);
   // k is up to 2048, so the per-warp lists bound it as well
@@ -451,32 +518,53 @@ static int launch_exact(hr_index* h, const int* qsel_dev, int nsel, int k, float
   if (k > 256) per_sm = 1;
   const int grid = h->num_sms * per_sm;
   const int64_t W = (int64_t)grid * 8;
-  int fsel = std::max(kExactF, std::min(64, (64 * 128 / std::max(k, 1)) / kExactF * kExactF));
+  const int fsel = exact_group(k);
   HR_TRY(h->ex_lists.ensure((size_t)fsel * W * k * 8));
   HR_TRY(h->ex_cnts.ensure((size_t)fsel * W * 4));
   HR_TRY(h->ex_tau.ensure((size_t)fsel * 8));
   if (smem_q > 200 * 1024) return set_err(HR_ERR_INVALID, "d too large for the exact scan kernel");
-  auto run = [&](auto scan, auto merge, int F, const int* qs, int ns) -> int {
+  auto run_scan = [&](auto scan, int F, const int* qs, int ns, int lo, int hi) -> int {
     const size_t smem = (size_t)F * h->ld * 4;
     HR_CUDA(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     scan<<<grid, 256, smem, st>>>((const T*)h->x, h->ntotal, h->ld, h->qpad.as<float>(), qs, ns, k,
-                                  h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>());
-    HR_LAUNCHED();
-    merge<<<ns, 256, 0, st>>>(h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>(), qs, W,
-                              k, h->id_base, D, I);
+                                  h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>(),
+                                  nsel_dev, lo, hi);
     HR_LAUNCHED();
     return HR_OK;
   };
+  auto run_merge = [&](auto merge, const int* qs, int ns) -> int {
+    merge<<<ns, 256, 0, st>>>(h->ex_lists.as<uint64_t>(), h->ex_cnts.as<int>(), h->ex_tau.as<unsigned long long>(), qs, W,
+                              k, h->id_base, D, I, nsel_dev);
+    HR_LAUNCHED();
+    return HR_OK;
+  };
+  const bool ip = h->metric == HR_METRIC_INNER_PRODUCT;
+  if (nsel_dev) {
+    const int cap = std::min(nsel, fsel);
+    HR_CUDA(cudaMemsetAsync(h->ex_tau.p, 0, (size_t)cap * 8, st));
+    if (ip) {
+      HR_TRY(run_scan(exact_scan_kernel<T, kMetricIP, 2>, 2, qsel_dev, cap, 1, 2));
+      if (cap > 2) HR_TRY(run_scan(exact_scan_kernel<T, kMetricIP, kExactF>, kExactF, qsel_dev, cap, 3, 1 << 30));
+      HR_TRY(run_merge(exact_merge_kernel<kMetricIP>, qsel_dev, cap));
+    } else {
+      HR_TRY(run_scan(exact_scan_kernel<T, kMetricL2, 2>, 2, qsel_dev, cap, 1, 2));
+      if (cap > 2) HR_TRY(run_scan(exact_scan_kernel<T, kMetricL2, kExactF>, kExactF, qsel_dev, cap, 3, 1 << 30));
+      HR_TRY(run_merge(exact_merge_kernel<kMetricL2>, qsel_dev, cap));
+    }
+    return HR_OK;
+  }
   for (int g0 = 0; g0 < nsel; g0 += fsel) {
     const int ns = std::min(fsel, nsel - g0);
     HR_CUDA(cudaMemsetAsync(h->ex_tau.p, 0, (size_t)ns * 8, st));
     const bool few = ns <= 2;
-    if (h->metric == HR_METRIC_INNER_PRODUCT) {
-      if (few) HR_TRY(run(exact_scan_kernel<T, kMetricIP, 2>, exact_merge_kernel<kMetricIP>, 2, qsel_dev + g0, ns));
-      else HR_TRY(run(exact_scan_kernel<T, kMetricIP, kExactF>, exact_merge_kernel<kMetricIP>, kExactF, qsel_dev + g0, ns));
+    if (ip) {
+      if (few) HR_TRY(run_scan(exact_scan_kernel<T, kMetricIP, 2>, 2, qsel_dev + g0, ns, 0, 0));
+      else HR_TRY(run_scan(exact_scan_kernel<T, kMetricIP, kExactF>, kExactF, qsel_dev + g0, ns, 0, 0));
+      HR_TRY(run_merge(exact_merge_kernel<kMetricIP>, qsel_dev + g0, ns));
     } else {
-      if (few) HR_TRY(run(exact_scan_kernel<T, kMetricL2, 2>, exact_merge_kernel<kMetricL2>, 2, qsel_dev + g0, ns));
-      else HR_TRY(run(exact_scan_kernel<T, kMetricL2, kExactF>, exact_merge_kernel<kMetricL2>, kExactF, qsel_dev + g0, ns));
+      if (few) HR_TRY(run_scan(exact_scan_kernel<T, kMetricL2, 2>, 2, qsel_dev + g0, ns, 0, 0));
+      else HR_TRY(run_scan(exact_scan_kernel<T, kMetricL2, kExactF>, kExactF, qsel_dev + g0, ns, 0, 0));
+      HR_TRY(run_merge(exact_merge_kernel<kMetricL2>, qsel_dev + g0, ns));
     }
   }
   return HR_OK;
@@ -502,50 +590,54 @@ static int launch_scan2(hr_index* h, const CUtensorMap& tq, const CUtensorMap& t
   return HR_OK;
 }
 
-// stage 1: every query of the batch, the best KL candidates; stage 2: the `ndeeper` queries listed in h->deeper,
-// all their candidates (up to kShortCap) against the bound of the thresholds alone
+// stage 1: every query of the batch, the best KL candidates; stage 2 (launched for every query, runs for the
+// `*ndeeper` queries stage 1 listed in h->deeper): all their candidates (up to kShortCap) against the bound of the
+// thresholds alone
 template <typename T>
 static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_acc, float* D, int64_t* I, cudaStream_t st,
-                          int ndeeper = 0) {
+                          bool stage2) {
   const int fk = filter_is_bf16(h) ? 2 : 1;   // how the filter rounded the query
-  const bool stage2 = ndeeper > 0;
   const int depth = stage2 ? kShortCap : KL;
-  const int blocks = stage2 ? ndeeper : nb;
   const size_t smem = (size_t)depth * 8;
   const int* n_in = stage2 ? h->short_tot.as<int>() : h->short_n.as<int>();
   const float* tp = stage2 ? h->tprime_tot.as<float>() : h->tprime.as<float>();
   const int* qsel = stage2 ? h->deeper.as<int>() : nullptr;
   int* deeper = stage2 ? nullptr : h->deeper.as<int>();
+  const int* nsel_dev = stage2 ? h->counters.as<int>() + 2 : nullptr;
   if (h->metric == HR_METRIC_INNER_PRODUCT)
-    rescore_finalize_kernel<T, kMetricIP><<<blocks, 256, smem, st>>>(
+    rescore_finalize_kernel<T, kMetricIP><<<nb, 256, smem, st>>>(
         (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), kShortCap, n_in, tp, depth, k, c_acc,
         fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(), h->counters.as<int>(), qsel,
-        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2, h->short_s.as<float>());
+        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2, h->short_s.as<float>(), nsel_dev);
   else
-    rescore_finalize_kernel<T, kMetricL2><<<blocks, 256, smem, st>>>(
+    rescore_finalize_kernel<T, kMetricL2><<<nb, 256, smem, st>>>(
         (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), kShortCap, n_in, tp, depth, k, c_acc,
         fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(), h->counters.as<int>(), qsel,
-        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2, h->short_s.as<float>());
+        h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2, h->short_s.as<float>(), nsel_dev);
   HR_LAUNCHED();
   return HR_OK;
 }
 
-// q_dev: fp32 [nq, d] on device; D_dev/I_dev: [nq, k] on device.  Synchronises `st` before returning.
-static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
-                            cudaStream_t st) {
-  const long long launches0 = g_launches.load();
-  h->stats = hr_scan_stats{};
+// ---- one chunk (<= kScanNqMax queries) of a dense search: everything is enqueued on `st`, nothing waits for the
+//      host.  The certificate's decisions are taken on the device: the second re-score stage and the exact
+//      fallback are always launched and run only for the queries the previous kernel listed.  chunk_finish()
+//      (after the caller synchronised `st`) reads the counters back, and completes the rare case of more than
+//      kExactDevCap fallback queries. ----
+static int chunk_enqueue(hr_index* h, const float* q_dev, int nb, int k, float* Db, int64_t* Ib, cudaStream_t st) {
+  h->pend = false;
   const float pad = h->metric == HR_METRIC_INNER_PRODUCT ? HR_NEG_INF : -HR_NEG_INF;
-  if (nq == 0) return HR_OK;
-  cudaEventRecord(h->ev[0], st);
   if (h->ntotal == 0) {
-    fill_pad_kernel<<<(int)std::min<int64_t>((nq * k + 255) / 256, 1024), 256, 0, st>>>(D_dev, I_dev, nq * k, pad);
+    fill_pad_kernel<<<(int)std::min<int64_t>(((int64_t)nb * k + 255) / 256, 1024), 256, 0, st>>>(Db, Ib, (int64_t)nb * k, pad);
     HR_LAUNCHED();
-    HR_CUDA(cudaStreamSynchronize(st));
-    h->stats.launches = g_launches.load() - launches0;
     return HR_OK;
   }
   const bool use_tc = (h->mode == HR_MODE_AUTO) && k <= 128;
+  if (h->mode == HR_MODE_AUTO && k > 128) {
+    static std::atomic<bool> warned{false};
+    if (!warned.exchange(true))
+      fprintf(stderr, "hr_b200: k = %d > 128: the tensor-core filter keeps at most 256 candidates per query, this search "
+                      "runs the exhaustive exact CUDA-core scan (same answers, ~10x slower per query)\n", k);
+  }
   // the bf16 shadow doubles the filter's error bound: a deeper shortlist keeps the certificate's margin
   const int KL = h->storage == HR_STORAGE_F32_SHADOW16 ? std::min(256, 2 * list_len_for_k(k)) : list_len_for_k(k);
   const int num_ctiles = (int)((h->ntotal + kScanBN - 1) / kScanBN);
@@ -553,153 +645,186 @@ static int index_search_dev(hr_index* h, const float* q_dev, int64_t nq, int k, 
   h->stats.mode_used = use_tc ? HR_MODE_AUTO : HR_MODE_EXACT_SIMT;
   h->stats.list_len = use_tc ? KL : k;
   h->stats.grid = use_tc ? grid : h->num_sms;
-  float scan_ms_total = 0.f;
+  // query rows materialised for the TMA (zero rows beyond nb): a full 128-row box, so that the SMs'
+  // re-reads of a small batch spread over 128 rows instead of hammering a few L2 lines
+  const int nbp = std::max(nb, tuning().q_rows);
+  HR_TRY(h->qpad.ensure((size_t)nbp * h->ld * 4));
+  if (filter_is_bf16(h)) HR_TRY(h->qh.ensure((size_t)nbp * h->ld * 2));
+  {
+    const int64_t tot = (int64_t)nbp * h->ld;
+    pad_queries_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 2048), 256, 0, st>>>(
+        q_dev, nb, nbp, h->d, h->ld, h->qpad.as<float>(), filter_is_bf16(h) ? h->qh.as<__nv_bfloat16>() : nullptr);
+    HR_LAUNCHED();
+  }
+  HR_TRY(h->ex_sel.ensure((size_t)nb * 4));
+  if (!use_tc) {
+    iota_kernel<<<(nb + 255) / 256, 256, 0, st>>>(h->ex_sel.as<int>(), nb, 0);
+    HR_LAUNCHED();
+    if (h->elem == 4) return launch_exact<float>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st);
+    return launch_exact<__nv_bfloat16>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st);
+  }
+  // ---- tensor-core filter scan ----
+  HR_TRY(h->lists.ensure((size_t)h->num_sms * nb * KL * sizeof(Cand)));
+  HR_TRY(h->cnts.ensure((size_t)h->num_sms * nb * 4));
+  HR_TRY(h->tau_g.ensure((size_t)nb * 4));
+  HR_TRY(h->short_rows.ensure((size_t)nb * kShortCap * 4));
+  HR_TRY(h->short_s.ensure((size_t)nb * kShortCap * 4));
+  HR_TRY(h->short_tot.ensure((size_t)nb * 4));
+  HR_TRY(h->tprime_tot.ensure((size_t)nb * 4));
+  HR_TRY(h->deeper.ensure((size_t)nb * 4));
+  HR_TRY(h->short_n.ensure((size_t)nb * 4));
+  HR_TRY(h->tprime.ensure((size_t)nb * 4));
+  HR_TRY(h->flagged.ensure((size_t)nb * 4));
+  HR_TRY(h->counters.ensure(16));
+  HR_CUDA(cudaMemsetAsync(h->tau_g.p, 0, (size_t)nb * 4, st));
+  HR_CUDA(cudaMemsetAsync(h->counters.p, 0, 16, st));
+  CUtensorMap tq, tx;
+  const void* qsrc = filter_is_bf16(h) ? (const void*)h->qh.p : (const void*)h->qpad.p;
+  HR_TRY(make_tmap(&tq, qsrc, nbp, h->ld, filter_elem(h), kScanBM));
+  HR_TRY(make_tmap(&tx, filter_rows(h), h->ntotal, h->ld, filter_elem(h), kScanBN));
+  ScanParams p;
+  p.N = h->ntotal;
+  p.nq = nb;
+  p.kblocks = (int)((size_t)h->ld * filter_elem(h) / 128);
+  p.KL = KL;
+  p.num_qtiles = (nb + kScanBM - 1) / kScanBM;
+  p.norms = h->norms;
+  p.lists = h->lists.as<Cand>();
+  p.cnts = h->cnts.as<int>();
+  p.tau_g = h->tau_g.as<unsigned int>();
+  p.pre_max = nullptr;
+  // batches of more than 128 queries run on CTA pairs (cta_group::2, 128-row corpus halves per CTA)
+  const bool use_pair = nb > kScanBM && h->num_sms >= 2 && !tuning().no_pair;
+  CUtensorMap tx2;
+  if (use_pair) HR_TRY(make_tmap(&tx2, filter_rows(h), h->ntotal, h->ld, filter_elem(h), 128));
+  auto run_scan = [&](int g) -> int {
+    if (use_pair) {
+      const int g2 = std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1);
+      if (!filter_is_bf16(h)) {
+        if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan2<0, 0>(h, tq, tx2, p, g2, st);
+        return launch_scan2<0, 1>(h, tq, tx2, p, g2, st);
+      }
+      if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan2<1, 0>(h, tq, tx2, p, g2, st);
+      return launch_scan2<1, 1>(h, tq, tx2, p, g2, st);
+    }
+    if (!filter_is_bf16(h)) {
+      if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<0, 0>(h, tq, tx, p, g, st);
+      return launch_scan<0, 1>(h, tq, tx, p, g, st);
+    }
+    if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<1, 0>(h, tq, tx, p, g, st);
+    return launch_scan<1, 1>(h, tq, tx, p, g, st);
+  };
+  // ---- threshold pre-pass over a strided sample of the corpus tiles.  The sample's KLs-th best score
+  //      seeds tau_g: about KLs*stride (= 4*KL) corpus rows beat it, so in the main pass only a handful
+  //      of scores per CTA pass the threshold and no per-CTA list ever fills.  Correctness never depends
+  //      on the seed: the certificate in rescore_finalize compares against the final threshold. ----
+  // Sample: at least pre_tiles tiles per scheduling unit (CTA or CTA pair) and at least every 32nd tile, at most
+  // kSeedCap tiles.  The seed is the j-th largest tile maximum, j >= 32: its corpus rank is Gamma(j, stride)
+  // distributed, mean about pre_rank * KL (or 32 * stride if that is larger), spread 1/sqrt(j).  A seed taken
+  // from fewer maxima (j = 8) landed inside the top 100 rows of a 5M-row shard for about 1 query in 10^4 and sent
+  // it to the exact scan: 16 ms for one query.
+  const int units = use_pair ? std::max(1, h->num_sms / 2) : h->num_sms;
+  int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (tuning().pre_tiles * units)));
+  stride = std::min(stride, 32);
+  stride = std::max(stride, (num_ctiles + kSeedCap - 1) / kSeedCap);
+  if (stride > 1) {
+    p.tile_stride = stride;
+    p.tile_count = (num_ctiles + stride - 1) / stride;
+    const int rk = tuning().pre_rank;   // target rank of the seed, in KL
+    const int jth = std::min(p.tile_count, std::max(32, (rk * KL + stride - 1) / stride));
+    HR_TRY(h->pre_max.ensure((size_t)p.tile_count * nb * 4));
+    p.pre_max = h->pre_max.as<float>();
+    const int gs = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1)
+                            : std::min(p.tile_count, h->num_sms);
+    HR_TRY(run_scan(gs));
+    scan_seed_kernel<<<nb, 256, 0, st>>>(h->pre_max.as<float>(), p.tile_count, nb, jth, h->tau_g.as<unsigned int>());
+    HR_LAUNCHED();
+    p.pre_max = nullptr;
+  }
+  p.tile_stride = 1;
+  p.tile_count = num_ctiles;
+  cudaEventRecord(h->ev[2], st);
+  const int gmain = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1) : grid;
+  HR_TRY(run_scan(gmain));
+  cudaEventRecord(h->ev[3], st);
+  h->stats.grid = gmain;
+  scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), gmain,
+                                        nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
+                                        h->tprime.as<float>(), h->counters.as<int>() + 1, nullptr,
+                                        h->short_tot.as<int>(), h->tprime_tot.as<float>(), h->short_s.as<float>());
+  HR_LAUNCHED();
+  // filter error bound = measured rounding residuals of both operands (rescore_finalize_kernel) + this
+  // relative allowance for the fp32 accumulation over ld terms
+  const float c_acc = 2.4e-7f * (float)h->ld;
+  const int cap = std::min(nb, exact_group(k));
+  if (h->elem == 4) {
+    HR_TRY(launch_rescore<float>(h, nb, KL, k, c_acc, Db, Ib, st, false));
+    HR_TRY(launch_rescore<float>(h, nb, KL, k, c_acc, Db, Ib, st, true));
+    HR_TRY(launch_exact<float>(h, h->flagged.as<int>(), cap, k, Db, Ib, st, h->counters.as<int>()));
+  } else {
+    HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_acc, Db, Ib, st, false));
+    HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_acc, Db, Ib, st, true));
+    HR_TRY(launch_exact<__nv_bfloat16>(h, h->flagged.as<int>(), cap, k, Db, Ib, st, h->counters.as<int>()));
+  }
+  HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 12, cudaMemcpyDeviceToHost, st));
+  h->pend = true;
+  h->pend_cap = cap;
+  h->pend_k = k;
+  h->pend_D = Db;
+  h->pend_I = Ib;
+  return HR_OK;
+}
 
+// After the caller synchronised the stream of chunk_enqueue: statistics, and the fallback queries beyond the
+// device-driven capacity (then *changed = true: D/I were modified by more work, which has been synchronised).
+static int chunk_finish(hr_index* h, cudaStream_t st, bool* changed) {
+  if (changed) *changed = false;
+  if (!h->pend) return HR_OK;
+  h->pend = false;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.scan_ms += ms;
+  const int nflag = h->h_counters[0];
+  h->stats.flagged += nflag;
+  h->stats.overflow += h->h_counters[1];
+  h->stats.deeper += h->h_counters[2];
+  if (nflag > h->pend_cap) {
+    const int rest = nflag - h->pend_cap;
+    if (h->elem == 4)
+      HR_TRY(launch_exact<float>(h, h->flagged.as<int>() + h->pend_cap, rest, h->pend_k, h->pend_D, h->pend_I, st));
+    else
+      HR_TRY(launch_exact<__nv_bfloat16>(h, h->flagged.as<int>() + h->pend_cap, rest, h->pend_k, h->pend_D, h->pend_I, st));
+    HR_CUDA(cudaStreamSynchronize(st));
+    if (changed) *changed = true;
+  }
+  return HR_OK;
+}
+
+// q_dev: fp32 [nq, d] on device; D_dev/I_dev: [nq, k] on device.  Enqueues the search; the caller synchronises
+// `st` and then calls index_search_finish.  Batches of more than kScanNqMax queries are processed in chunks, each
+// synchronised here (the per-query scratch is per chunk).
+static int index_search_enqueue(hr_index* h, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                                cudaStream_t st) {
+  h->launches0 = g_launches.load();
+  h->stats = hr_scan_stats{};
+  h->pend = false;
+  if (nq == 0) return HR_OK;
+  cudaEventRecord(h->ev[0], st);
   for (int64_t q0 = 0; q0 < nq; q0 += kScanNqMax) {
     const int nb = (int)std::min<int64_t>(kScanNqMax, nq - q0);
-    float* Db = D_dev + q0 * k;
-    int64_t* Ib = I_dev + q0 * k;
-    // query rows materialised for the TMA (zero rows beyond nb): a full 128-row box, so that the SMs'
-    // re-reads of a small batch spread over 128 rows instead of hammering a few L2 lines
-    const int nbp = std::max(nb, tuning().q_rows);
-    HR_TRY(h->qpad.ensure((size_t)nbp * h->ld * 4));
-    if (filter_is_bf16(h)) HR_TRY(h->qh.ensure((size_t)nbp * h->ld * 2));
-    {
-      const int64_t tot = (int64_t)nbp * h->ld;
-      pad_queries_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 2048), 256, 0, st>>>(
-          q_dev + q0 * h->d, nb, nbp, h->d, h->ld, h->qpad.as<float>(),
-          filter_is_bf16(h) ? h->qh.as<__nv_bfloat16>() : nullptr);
-      HR_LAUNCHED();
-    }
-    HR_TRY(h->ex_sel.ensure((size_t)nb * 4));
-    if (!use_tc) {
-      iota_kernel<<<(nb + 255) / 256, 256, 0, st>>>(h->ex_sel.as<int>(), nb, 0);
-      HR_LAUNCHED();
-      if (h->elem == 4) HR_TRY(launch_exact<float>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st));
-      else HR_TRY(launch_exact<__nv_bfloat16>(h, h->ex_sel.as<int>(), nb, k, Db, Ib, st));
-      continue;
-    }
-    // ---- tensor-core filter scan ----
-    HR_TRY(h->lists.ensure((size_t)h->num_sms * nb * KL * sizeof(Cand)));
-    HR_TRY(h->cnts.ensure((size_t)h->num_sms * nb * 4));
-    HR_TRY(h->tau_g.ensure((size_t)nb * 4));
-    HR_TRY(h->short_rows.ensure((size_t)nb * kShortCap * 4));
-    HR_TRY(h->short_s.ensure((size_t)nb * kShortCap * 4));
-    HR_TRY(h->short_tot.ensure((size_t)nb * 4));
-    HR_TRY(h->tprime_tot.ensure((size_t)nb * 4));
-    HR_TRY(h->deeper.ensure((size_t)nb * 4));
-    HR_TRY(h->short_n.ensure((size_t)nb * 4));
-    HR_TRY(h->tprime.ensure((size_t)nb * 4));
-    HR_TRY(h->flagged.ensure((size_t)nb * 4));
-    HR_TRY(h->counters.ensure(16));
-    HR_CUDA(cudaMemsetAsync(h->tau_g.p, 0, (size_t)nb * 4, st));
-    HR_CUDA(cudaMemsetAsync(h->counters.p, 0, 16, st));
-    CUtensorMap tq, tx;
-    const void* qsrc = filter_is_bf16(h) ? (const void*)h->qh.p : (const void*)h->qpad.p;
-    HR_TRY(make_tmap(&tq, qsrc, nbp, h->ld, filter_elem(h), kScanBM));
-    HR_TRY(make_tmap(&tx, filter_rows(h), h->ntotal, h->ld, filter_elem(h), kScanBN));
-    ScanParams p;
-    p.N = h->ntotal;
-    p.nq = nb;
-    p.kblocks = (int)((size_t)h->ld * filter_elem(h) / 128);
-    p.KL = KL;
-    p.num_qtiles = (nb + kScanBM - 1) / kScanBM;
-    p.norms = h->norms;
-    p.lists = h->lists.as<Cand>();
-    p.cnts = h->cnts.as<int>();
-    p.tau_g = h->tau_g.as<unsigned int>();
-    p.pre_max = nullptr;
-    // batches of more than 128 queries run on CTA pairs (cta_group::2, 128-row corpus halves per CTA)
-    const bool use_pair = nb > kScanBM && h->num_sms >= 2 && !tuning().no_pair;
-    CUtensorMap tx2;
-    if (use_pair) HR_TRY(make_tmap(&tx2, filter_rows(h), h->ntotal, h->ld, filter_elem(h), 128));
-    auto run_scan = [&](int g) -> int {
-      if (use_pair) {
-        const int g2 = std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1);
-        if (!filter_is_bf16(h)) {
-          if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan2<0, 0>(h, tq, tx2, p, g2, st);
-          return launch_scan2<0, 1>(h, tq, tx2, p, g2, st);
-        }
-        if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan2<1, 0>(h, tq, tx2, p, g2, st);
-        return launch_scan2<1, 1>(h, tq, tx2, p, g2, st);
-      }
-      if (!filter_is_bf16(h)) {
-        if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<0, 0>(h, tq, tx, p, g, st);
-        return launch_scan<0, 1>(h, tq, tx, p, g, st);
-      }
-      if (h->metric == HR_METRIC_INNER_PRODUCT) return launch_scan<1, 0>(h, tq, tx, p, g, st);
-      return launch_scan<1, 1>(h, tq, tx, p, g, st);
-    };
-    // ---- threshold pre-pass over a strided sample of the corpus tiles.  The sample's KLs-th best score
-    //      seeds tau_g: about KLs*stride (= 4*KL) corpus rows beat it, so in the main pass only a handful
-    //      of scores per CTA pass the threshold and no per-CTA list ever fills.  Correctness never depends
-    //      on the seed: the certificate in rescore_finalize compares against the final threshold. ----
-    // Sample: at least pre_tiles tiles per scheduling unit (CTA or CTA pair) and at least every 32nd tile, at most
-    // kSeedCap tiles.  The seed is the j-th largest tile maximum, j >= 32: its corpus rank is Gamma(j, stride)
-    // distributed, mean about pre_rank * KL (or 32 * stride if that is larger), spread 1/sqrt(j).  A seed taken
-    // from fewer maxima (j = 8) landed inside the top 100 rows of a 5M-row shard for about 1 query in 10^4 and sent
-    // it to the exact scan: 16 ms for one query.
-    const int units = use_pair ? std::max(1, h->num_sms / 2) : h->num_sms;
-    int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (tuning().pre_tiles * units)));
-    stride = std::min(stride, 32);
-    stride = std::max(stride, (num_ctiles + kSeedCap - 1) / kSeedCap);
-    if (stride > 1) {
-      p.tile_stride = stride;
-      p.tile_count = (num_ctiles + stride - 1) / stride;
-      const int rk = tuning().pre_rank;   // target rank of the seed, in KL
-      const int jth = std::min(p.tile_count, std::max(32, (rk * KL + stride - 1) / stride));
-      HR_TRY(h->pre_max.ensure((size_t)p.tile_count * nb * 4));
-      p.pre_max = h->pre_max.as<float>();
-      const int gs = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1)
-                              : std::min(p.tile_count, h->num_sms);
-      HR_TRY(run_scan(gs));
-      scan_seed_kernel<<<nb, 256, 0, st>>>(h->pre_max.as<float>(), p.tile_count, nb, jth, h->tau_g.as<unsigned int>());
-      HR_LAUNCHED();
-      p.pre_max = nullptr;
-    }
-    p.tile_stride = 1;
-    p.tile_count = num_ctiles;
-    cudaEventRecord(h->ev[2], st);
-    const int gmain = use_pair ? std::max(2, std::min(2 * p.tile_count, h->num_sms) & ~1) : grid;
-    HR_TRY(run_scan(gmain));
-    cudaEventRecord(h->ev[3], st);
-    h->stats.grid = gmain;
-    scan_merge_kernel<<<nb, 256, 0, st>>>(h->lists.as<Cand>(), h->cnts.as<int>(), h->tau_g.as<unsigned int>(), gmain,
-                                          nb, KL, h->short_rows.as<uint32_t>(), h->short_n.as<int>(),
-                                          h->tprime.as<float>(), h->counters.as<int>() + 1, nullptr,
-                                          h->short_tot.as<int>(), h->tprime_tot.as<float>(), h->short_s.as<float>());
-    HR_LAUNCHED();
-    // filter error bound = measured rounding residuals of both operands (rescore_finalize_kernel) + this
-    // relative allowance for the fp32 accumulation over ld terms
-    const float c_acc = 2.4e-7f * (float)h->ld;
-    if (h->elem == 4) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_acc, Db, Ib, st));
-    else HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_acc, Db, Ib, st));
-    HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 12, cudaMemcpyDeviceToHost, st));
-    HR_CUDA(cudaStreamSynchronize(st));
-    if (h->h_counters[2] > 0) {
-      // certificate failed on the best KL candidates of a few queries: re-score all their candidates
-      h->stats.deeper += h->h_counters[2];
-      if (h->elem == 4) HR_TRY(launch_rescore<float>(h, nb, KL, k, c_acc, Db, Ib, st, h->h_counters[2]));
-      else HR_TRY(launch_rescore<__nv_bfloat16>(h, nb, KL, k, c_acc, Db, Ib, st, h->h_counters[2]));
-      HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 8, cudaMemcpyDeviceToHost, st));
+    HR_TRY(chunk_enqueue(h, q_dev + q0 * h->d, nb, k, D_dev + q0 * k, I_dev + q0 * k, st));
+    if (q0 + kScanNqMax < nq) {
       HR_CUDA(cudaStreamSynchronize(st));
-    }
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) scan_ms_total += ms;
-    const int nflag = h->h_counters[0];
-    h->stats.flagged += nflag;
-    h->stats.overflow += h->h_counters[1];
-    if (nflag > 0) {
-      if (h->elem == 4) HR_TRY(launch_exact<float>(h, h->flagged.as<int>(), nflag, k, Db, Ib, st));
-      else HR_TRY(launch_exact<__nv_bfloat16>(h, h->flagged.as<int>(), nflag, k, Db, Ib, st));
+      HR_TRY(chunk_finish(h, st, nullptr));
     }
   }
   cudaEventRecord(h->ev[1], st);
-  HR_CUDA(cudaStreamSynchronize(st));
+  return HR_OK;
+}
+static int index_search_finish(hr_index* h, cudaStream_t st, bool* changed) {
+  HR_TRY(chunk_finish(h, st, changed));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->stats.total_ms = ms;
-  h->stats.scan_ms = scan_ms_total;
-  h->stats.launches = g_launches.load() - launches0;
+  h->stats.launches = g_launches.load() - h->launches0;
   return HR_OK;
 }
 
@@ -711,16 +836,28 @@ extern "C" int hr_index_search(hr_index* h, const float* q, int64_t nq, int k, f
   if (nq == 0) return HR_OK;
   if (!q || !D || !I) return set_err(HR_ERR_INVALID, "null q / D / I");
   HR_DEVICE(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
   cudaStream_t st = (cudaStream_t)stream;
-  if (io_on_device) return index_search_dev(h, q, nq, k, D, I, st);
+  if (io_on_device) {
+    HR_TRY(index_search_enqueue(h, q, nq, k, D, I, st));
+    HR_CUDA(cudaStreamSynchronize(st));
+    return index_search_finish(h, st, nullptr);
+  }
   HR_TRY(h->io_q.ensure((size_t)nq * h->d * 4));
   HR_TRY(h->io_D.ensure((size_t)nq * k * 4));
   HR_TRY(h->io_I.ensure((size_t)nq * k * 8));
   HR_CUDA(cudaMemcpyAsync(h->io_q.p, q, (size_t)nq * h->d * 4, cudaMemcpyHostToDevice, st));
-  HR_TRY(index_search_dev(h, h->io_q.as<float>(), nq, k, h->io_D.as<float>(), h->io_I.as<int64_t>(), st));
+  HR_TRY(index_search_enqueue(h, h->io_q.as<float>(), nq, k, h->io_D.as<float>(), h->io_I.as<int64_t>(), st));
   HR_CUDA(cudaMemcpyAsync(D, h->io_D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
   HR_CUDA(cudaMemcpyAsync(I, h->io_I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
   HR_CUDA(cudaStreamSynchronize(st));
+  bool changed = false;
+  HR_TRY(index_search_finish(h, st, &changed));
+  if (changed) {
+    HR_CUDA(cudaMemcpyAsync(D, h->io_D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(cudaMemcpyAsync(I, h->io_I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(cudaStreamSynchronize(st));
+  }
   return HR_OK;
 }
 
@@ -812,23 +949,30 @@ extern "C" int hr_index_load(const char* path, int device, int storage_dtype, hr
 struct hr_bm25 {
   int device = 0;
   int num_sms = 148;
-  int64_t N = 0, V = 0, nnz = 0, id_base = 0;
-  int64_t* indptr = nullptr;
-  int32_t* post_doc = nullptr;
-  float* post_imp = nullptr;
+  int64_t N = 0, V = 0, nnz = 0, nnz_pad = 0, id_base = 0;
+  int64_t* indptr = nullptr;   // [V+1] unpadded offsets: list lengths / df
+  int64_t* pstart = nullptr;   // [V+1] padded list starts (multiples of 4)
+  int32_t* post_doc = nullptr; // [nnz_pad + 4]
+  float* post_imp = nullptr;   // [nnz_pad + 4]
   float* idf = nullptr;
-  DevBuf keys, ns, io_qi, io_qt, io_S, io_I, touched, plan_nt, plan_start, plan_len, plan_wgt, plan_cur, plan_coarse, tau;
+  DevBuf keys, ns, io_qi, io_qt, io_S, io_I, touched, plan_nt, plan_start, plan_len, plan_wgt, plan_cur, plan_coarse, tau,
+      jobctr, plan_err;
+  int* h_plan_err = nullptr;   // pinned copy of plan_err (queries with too many distinct terms in the last search)
+  std::mutex mu;               // one search at a time per handle (the scratch above is per handle)
 };
 
 extern "C" int hr_bm25_destroy(hr_bm25* h) {
   if (!h) return HR_OK;
   DeviceGuard g(h->device);
   if (h->indptr) cudaFree(h->indptr);
+  if (h->pstart) cudaFree(h->pstart);
   if (h->post_doc) cudaFree(h->post_doc);
   if (h->post_imp) cudaFree(h->post_imp);
   if (h->idf) cudaFree(h->idf);
+  if (h->h_plan_err) cudaFreeHost(h->h_plan_err);
   DevBuf* bufs[] = {&h->keys,    &h->ns,         &h->io_qi,    &h->io_qt,    &h->io_S,     &h->io_I, &h->touched,
-                    &h->plan_nt, &h->plan_start, &h->plan_len, &h->plan_wgt, &h->plan_cur, &h->plan_coarse, &h->tau};
+                    &h->plan_nt, &h->plan_start, &h->plan_len, &h->plan_wgt, &h->plan_cur, &h->plan_coarse, &h->tau,
+                    &h->jobctr,  &h->plan_err};
   for (DevBuf* b : bufs) b->release();
   delete h;
   return HR_OK;
@@ -839,6 +983,53 @@ extern "C" int64_t hr_bm25_nnz(const hr_bm25* h) { return h ? h->nnz : -1; }
 extern "C" int hr_bm25_set_id_base(hr_bm25* h, int64_t id_base) {
   if (!h) return set_err(HR_ERR_INVALID, "null bm25");
   h->id_base = id_base;
+  return HR_OK;
+}
+
+// padded list starts from the (host) CSR offsets: every list begins at a multiple of 4
+static bool padded_starts(const std::vector<int64_t>& indptr, std::vector<int64_t>& pstart) {
+  const size_t V = indptr.size() - 1;
+  pstart.resize(V + 1);
+  int64_t p = 0;
+  for (size_t t = 0; t < V; ++t) {
+    const int64_t len = indptr[t + 1] - indptr[t];
+    if (len < 0 || len > (int64_t)0xFFFFFFF0ll) return false;
+    pstart[t] = p;
+    p += (len + 3) & ~(int64_t)3;
+  }
+  pstart[V] = p;
+  return true;
+}
+
+// handle with device arrays for (N, V, nnz) allocated; postings not yet filled
+static int bm25_alloc(hr_bm25** out, int device, int64_t n_docs, int64_t vocab, const std::vector<int64_t>& h_indptr,
+                      const std::vector<int64_t>& h_pstart) {
+  hr_bm25* h = new hr_bm25();
+  h->device = device;
+  h->N = n_docs;
+  h->V = vocab;
+  h->nnz = h_indptr[vocab];
+  h->nnz_pad = h_pstart[vocab];
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  const size_t np = (size_t)h->nnz_pad + 4;   // +4: sentinels behind the last list
+  if (cudaMalloc((void**)&h->indptr, (size_t)(vocab + 1) * 8) != cudaSuccess ||
+      cudaMalloc((void**)&h->pstart, (size_t)(vocab + 1) * 8) != cudaSuccess ||
+      cudaMalloc((void**)&h->post_doc, np * 4) != cudaSuccess || cudaMalloc((void**)&h->post_imp, np * 4) != cudaSuccess ||
+      cudaMalloc((void**)&h->idf, (size_t)vocab * 4) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_plan_err, 4) != cudaSuccess) {
+    (void)cudaGetLastError();
+    hr_bm25_destroy(h);
+    return set_err(HR_ERR_NOMEM, "cudaMalloc failed for the BM25 index");
+  }
+  *h->h_plan_err = 0;
+  if (cudaMemcpy(h->indptr, h_indptr.data(), (size_t)(vocab + 1) * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->pstart, h_pstart.data(), (size_t)(vocab + 1) * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+    (void)cudaGetLastError();
+    hr_bm25_destroy(h);
+    return set_err(HR_ERR_CUDA, "copy of BM25 tables failed");
+  }
+  *out = h;
   return HR_OK;
 }
 
@@ -857,7 +1048,6 @@ extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, co
   if (device < 0 || device >= ndev) return set_err(HR_ERR_INVALID, "device ordinal out of range");
   HR_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
-  const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   // host copy of indptr (df, nnz)
   std::vector<int64_t> h_indptr((size_t)vocab + 1);
   if (is_device) {
@@ -867,7 +1057,9 @@ extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, co
     memcpy(h_indptr.data(), indptr, (size_t)(vocab + 1) * 8);
   }
   const int64_t nnz = h_indptr[vocab];
-  if (h_indptr[0] != 0 || nnz < 0) return set_err(HR_ERR_INVALID, "indptr must start at 0 and be non-decreasing");
+  std::vector<int64_t> h_pstart;
+  if (h_indptr[0] != 0 || nnz < 0 || !padded_starts(h_indptr, h_pstart))
+    return set_err(HR_ERR_INVALID, "indptr must start at 0 and be non-decreasing");
   if (nnz > 0 && (!post_doc || !post_tf || !doc_len)) return set_err(HR_ERR_INVALID, "null postings");
   std::vector<int64_t> h_df;
   if (df_global) {
@@ -900,45 +1092,36 @@ extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, co
       h_idf[t] = (float)v;
     }
   }
-  hr_bm25* h = new hr_bm25();
-  h->device = device;
-  h->N = n_docs;
-  h->V = vocab;
-  h->nnz = nnz;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
-  int32_t* d_tf = nullptr;
-  int32_t* d_dl = nullptr;
+  hr_bm25* h = nullptr;
+  HR_TRY(bm25_alloc(&h, device, n_docs, vocab, h_indptr, h_pstart));
+  DevBuf d_doc, d_tf, d_dl, d_bad;
   auto fail = [&](int code, const char* msg) {
     (void)cudaGetLastError();
-    if (d_tf) cudaFree(d_tf);
-    if (d_dl) cudaFree(d_dl);
+    d_doc.release();
+    d_tf.release();
+    d_dl.release();
+    d_bad.release();
     hr_bm25_destroy(h);
     return set_err(code, msg);
   };
-  const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
-  const size_t nd = (size_t)std::max<int64_t>(n_docs, 1);
-  if (cudaMalloc((void**)&h->indptr, (size_t)(vocab + 1) * 8) != cudaSuccess ||
-      cudaMalloc((void**)&h->post_doc, (nz + 4) * 4) != cudaSuccess ||   // +4: the window kernel reads 16-byte groups
-      cudaMalloc((void**)&h->post_imp, (nz + 4) * 4) != cudaSuccess || cudaMalloc((void**)&h->idf, (size_t)vocab * 4) != cudaSuccess)
-    return fail(HR_ERR_NOMEM, "cudaMalloc failed for the BM25 index");
-  double avgdl = avgdl_global;
-  if (cudaMemcpyAsync(h->indptr, h_indptr.data(), (size_t)(vocab + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-      cudaMemcpyAsync(h->idf, h_idf.data(), (size_t)vocab * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
+  if (cudaMemcpyAsync(h->idf, h_idf.data(), (size_t)vocab * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
     return fail(HR_ERR_CUDA, "copy of BM25 tables failed");
+  double avgdl = avgdl_global;
+  unsigned long long n_bad = 0;
   if (nnz > 0) {
-    if (cudaMemcpyAsync(h->post_doc, post_doc, (size_t)nnz * 4, kind, st) != cudaSuccess)
-      return fail(HR_ERR_CUDA, "copy of postings failed");
+    const int32_t* docp = post_doc;
     const int32_t* tfp = post_tf;
     const int32_t* dlp = doc_len;
     if (!is_device) {
-      if (cudaMalloc((void**)&d_tf, (size_t)nnz * 4) != cudaSuccess || cudaMalloc((void**)&d_dl, nd * 4) != cudaSuccess)
+      if (d_doc.ensure((size_t)nnz * 4) || d_tf.ensure((size_t)nnz * 4) || d_dl.ensure((size_t)std::max<int64_t>(n_docs, 1) * 4))
         return fail(HR_ERR_NOMEM, "cudaMalloc failed for BM25 build scratch");
-      if (cudaMemcpyAsync(d_tf, post_tf, (size_t)nnz * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-          cudaMemcpyAsync(d_dl, doc_len, (size_t)n_docs * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      if (cudaMemcpyAsync(d_doc.p, post_doc, (size_t)nnz * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaMemcpyAsync(d_tf.p, post_tf, (size_t)nnz * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaMemcpyAsync(d_dl.p, doc_len, (size_t)n_docs * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
         return fail(HR_ERR_CUDA, "copy of BM25 build inputs failed");
-      tfp = d_tf;
-      dlp = d_dl;
+      docp = d_doc.as<int32_t>();
+      tfp = d_tf.as<int32_t>();
+      dlp = d_dl.as<int32_t>();
     }
     if (!(avgdl > 0.0)) {
       // local average document length (fp64 on the host, like the oracle)
@@ -950,15 +1133,28 @@ extern "C" int hr_bm25_create(const int64_t* indptr, const int32_t* post_doc, co
       for (int64_t i = 0; i < n_docs; ++i) s += (double)h_dl[i];
       avgdl = n_docs ? s / (double)n_docs : 0.0;
     }
+    if (d_bad.ensure(8) || cudaMemsetAsync(d_bad.p, 0, 8, st) != cudaSuccess)
+      return fail(HR_ERR_NOMEM, "cudaMalloc failed for BM25 build scratch");
     const int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)h->num_sms * 16);
-    bm25_impact_kernel<<<blocks, 256, 0, st>>>(h->post_doc, tfp, dlp, nnz, (double)k1, (double)b, avgdl, h->post_imp);
+    bm25_pad_impact_kernel<<<blocks, 256, 0, st>>>(h->indptr, h->pstart, docp, tfp, dlp, nnz, vocab, n_docs, (double)k1,
+                                                   (double)b, avgdl, h->post_doc, h->post_imp,
+                                                   d_bad.as<unsigned long long>());
     g_launches.fetch_add(1);
-    if (cudaGetLastError() != cudaSuccess) return fail(HR_ERR_CUDA, "bm25_impact_kernel launch failed");
+    if (cudaGetLastError() != cudaSuccess) return fail(HR_ERR_CUDA, "bm25_pad_impact_kernel launch failed");
+    if (cudaMemcpyAsync(&n_bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      return fail(HR_ERR_CUDA, "BM25 build failed");
   }
-  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(HR_ERR_CUDA, "BM25 build failed");
-  if (d_tf) cudaFree(d_tf);
-  if (d_dl) cudaFree(d_dl);
-  d_tf = d_dl = nullptr;
+  bm25_pad_sentinels_kernel<<<(unsigned)std::min<int64_t>((vocab + 255) / 256, (int64_t)h->num_sms * 16), 256, 0, st>>>(
+      h->indptr, h->pstart, vocab, 4, h->post_doc, h->post_imp);
+  g_launches.fetch_add(1);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    return fail(HR_ERR_CUDA, "BM25 build failed");
+  if (n_bad)
+    return fail(HR_ERR_INVALID, "bad CSR: doc ids must lie in [0, n_docs) and ascend strictly inside a posting list, tf > 0");
+  d_doc.release();
+  d_tf.release();
+  d_dl.release();
+  d_bad.release();
   *out = h;
   return HR_OK;
 }
@@ -1072,8 +1268,9 @@ extern "C" int hr_bm25_create_from_tokens(const int32_t* term_ids, const int32_t
 }
 
 // ---- persistence: the BM25 sidecar the reference never wrote ---------------------
-// "HRBM25\0\1" | int64 N, V, nnz, id_base | indptr int64[V+1] | idf fp32[V] | post_doc int32[nnz] | post_imp fp32[nnz]
-static const char kBm25Magic[8] = {'H', 'R', 'B', 'M', '2', '5', 0, 1};
+// "HRBM25\0\2" | int64 N, V, nnz, id_base, nnz_pad | indptr int64[V+1] | idf fp32[V] |
+// post_doc int32[nnz_pad] | post_imp fp32[nnz_pad]   (padded lists: bm25.cuh; pstart is derived from indptr)
+static const char kBm25Magic[8] = {'H', 'R', 'B', 'M', '2', '5', 0, 2};
 
 static bool dev_to_file(FILE* f, const void* dev, size_t bytes, std::vector<char>& buf) {
   const size_t chunk = (size_t)64 << 20;
@@ -1099,13 +1296,15 @@ static bool file_to_dev(FILE* f, void* dev, size_t bytes, std::vector<char>& buf
 extern "C" int hr_bm25_save(hr_bm25* h, const char* path) {
   if (!h || !path) return set_err(HR_ERR_INVALID, "null argument");
   HR_DEVICE(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
   FILE* f = fopen(path, "wb");
   if (!f) return set_err(HR_ERR_IO, std::string("cannot open for writing: ") + path);
-  int64_t hdr[4] = {h->N, h->V, h->nnz, h->id_base};
+  int64_t hdr[5] = {h->N, h->V, h->nnz, h->id_base, h->nnz_pad};
   std::vector<char> buf;
-  bool ok = fwrite(kBm25Magic, 1, 8, f) == 8 && fwrite(hdr, 8, 4, f) == 4 &&
+  bool ok = fwrite(kBm25Magic, 1, 8, f) == 8 && fwrite(hdr, 8, 5, f) == 5 &&
             dev_to_file(f, h->indptr, (size_t)(h->V + 1) * 8, buf) && dev_to_file(f, h->idf, (size_t)h->V * 4, buf) &&
-            dev_to_file(f, h->post_doc, (size_t)h->nnz * 4, buf) && dev_to_file(f, h->post_imp, (size_t)h->nnz * 4, buf);
+            dev_to_file(f, h->post_doc, (size_t)h->nnz_pad * 4, buf) &&
+            dev_to_file(f, h->post_imp, (size_t)h->nnz_pad * 4, buf);
   if (fclose(f) != 0) ok = false;
   if (!ok) return set_err(HR_ERR_IO, std::string("write failed: ") + path);
   return HR_OK;
@@ -1121,39 +1320,53 @@ extern "C" int hr_bm25_load(const char* path, int device, hr_bm25** out) {
   FILE* f = fopen(path, "rb");
   if (!f) return set_err(HR_ERR_IO, std::string("cannot open BM25 index file: ") + path);
   char magic[8];
-  int64_t hdr[4] = {0, 0, 0, 0};
-  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kBm25Magic, 8) != 0 || fread(hdr, 8, 4, f) != 4 || hdr[0] < 0 ||
-      hdr[1] <= 0 || hdr[2] < 0) {
+  int64_t hdr[5] = {0, 0, 0, 0, 0};
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kBm25Magic, 8) != 0 || fread(hdr, 8, 5, f) != 5 || hdr[0] < 0 ||
+      hdr[0] >= (int64_t)0x7FFFFFF0ll || hdr[1] <= 0 || hdr[1] > (int64_t)0x7FFFFFFFll || hdr[2] < 0 || hdr[4] < hdr[2]) {
     fclose(f);
-    return set_err(HR_ERR_IO, std::string("not a BM25 index file (HRBM25 v1) or corrupt header: ") + path);
+    return set_err(HR_ERR_IO, std::string("not a BM25 index file (HRBM25 v2) or corrupt header: ") + path);
+  }
+  const int64_t V = hdr[1];
+  std::vector<int64_t> h_indptr((size_t)V + 1), h_pstart;
+  bool ok = fread(h_indptr.data(), 8, (size_t)V + 1, f) == (size_t)V + 1 && h_indptr[0] == 0 && h_indptr[V] == hdr[2] &&
+            padded_starts(h_indptr, h_pstart) && h_pstart[V] == hdr[4];
+  if (!ok) {
+    fclose(f);
+    return set_err(HR_ERR_IO, std::string("corrupt BM25 index file (term offsets): ") + path);
   }
   HR_DEVICE(device);
-  hr_bm25* h = new hr_bm25();
-  h->device = device;
-  h->N = hdr[0];
-  h->V = hdr[1];
-  h->nnz = hdr[2];
-  h->id_base = hdr[3];
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
-  const size_t nz = (size_t)std::max<int64_t>(h->nnz, 1);
-  std::vector<char> buf;
-  bool ok = cudaMalloc((void**)&h->indptr, (size_t)(h->V + 1) * 8) == cudaSuccess &&
-            cudaMalloc((void**)&h->idf, (size_t)h->V * 4) == cudaSuccess &&
-            cudaMalloc((void**)&h->post_doc, (nz + 4) * 4) == cudaSuccess &&
-            cudaMalloc((void**)&h->post_imp, (nz + 4) * 4) == cudaSuccess;
-  if (!ok) {
-    (void)cudaGetLastError();
+  hr_bm25* h = nullptr;
+  int rc = bm25_alloc(&h, device, hdr[0], V, h_indptr, h_pstart);
+  if (rc != HR_OK) {
     fclose(f);
-    hr_bm25_destroy(h);
-    return set_err(HR_ERR_NOMEM, "cudaMalloc failed for the BM25 index");
+    return rc;
   }
-  ok = file_to_dev(f, h->indptr, (size_t)(h->V + 1) * 8, buf) && file_to_dev(f, h->idf, (size_t)h->V * 4, buf) &&
-       file_to_dev(f, h->post_doc, (size_t)h->nnz * 4, buf) && file_to_dev(f, h->post_imp, (size_t)h->nnz * 4, buf);
+  h->id_base = hdr[3];
+  std::vector<char> buf;
+  ok = file_to_dev(f, h->idf, (size_t)V * 4, buf) && file_to_dev(f, h->post_doc, (size_t)h->nnz_pad * 4, buf) &&
+       file_to_dev(f, h->post_imp, (size_t)h->nnz_pad * 4, buf);
   fclose(f);
   if (!ok) {
     hr_bm25_destroy(h);
     return set_err(HR_ERR_IO, std::string("truncated BM25 index file: ") + path);
+  }
+  // what the scoring kernels rely on: ascending in-range doc ids, sentinel padding
+  DevBuf bad;
+  unsigned long long n_bad = 1;
+  if (bad.ensure(8) == HR_OK && cudaMemset(bad.p, 0, 8) == cudaSuccess) {
+    bm25_check_padded_kernel<<<h->num_sms * 8, 256>>>(h->indptr, h->pstart, h->post_doc, V, h->N,
+                                                     bad.as<unsigned long long>());
+    // the 4 sentinels behind the last list are not part of the file
+    bm25_pad_sentinels_kernel<<<(unsigned)std::min<int64_t>((V + 255) / 256, (int64_t)h->num_sms * 16), 256>>>(
+        h->indptr, h->pstart, V, 4, h->post_doc, h->post_imp);
+    g_launches.fetch_add(2);
+    if (cudaMemcpy(&n_bad, bad.p, 8, cudaMemcpyDeviceToHost) != cudaSuccess) n_bad = 1;
+  }
+  bad.release();
+  if (n_bad) {
+    (void)cudaGetLastError();
+    hr_bm25_destroy(h);
+    return set_err(HR_ERR_IO, std::string("corrupt BM25 index file (posting lists): ") + path);
   }
   *out = h;
   return HR_OK;
@@ -1173,20 +1386,35 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   }
   int kcp = 32;
   while (kcp < k) kcp <<= 1;
-  const int smem = bs_smem_bytes(kcp);
-  const int slice_docs = bs_slice_docs(kcp);
+  const bool sweep = tuning().bm25_impl == 0;
+  const bool wide = tuning().bm25_wide != 0;
+  const int slice_docs = !sweep ? bs_slice_docs(kcp)
+                                : (kcp <= 64 ? (wide ? kSwSliceWideA : kSwSliceA) : (wide ? kSwSliceWideB : kSwSliceB));
   const int64_t nsl = std::max<int64_t>(1, (h->N + slice_docs - 1) / slice_docs);   // slices; nsl + 1 boundaries
   const int64_t nbc = (nsl + kBsCoarse - 1) / kBsCoarse + 1;                    // coarse boundaries
   const size_t nterm_slots = (size_t)std::max<int64_t>(n_terms, 1);
   const size_t cur_bytes = nterm_slots * (size_t)(nsl + 1) * 4;
   if (cur_bytes > ((size_t)16 << 30))
     return set_err(HR_ERR_INVALID, "bm25: query batch too large for the cursor table (split the batch)");
-  // spans per query: ~8 waves of CTAs over the machine (kBsCtasPerSm resident per SM), bounded by the merge capacity;
-  // a CTA wants at least one slice per warp
-  const int waves = tuning().bm25_waves;
-  int64_t S = ((int64_t)waves * kBsCtasPerSm * h->num_sms + nq - 1) / nq;
-  S = std::max<int64_t>(1, std::min<int64_t>({S, (nsl + kBsWarps - 1) / kBsWarps, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
-  const int spc = (int)((nsl + S - 1) / S);
+  int64_t S;   // doc windows (spans) per query
+  int spc;     // slices per window
+  if (sweep) {
+    // jobs = (window, query), one warp each, drawn window-major by the resident warps.  Enough jobs for a
+    // balanced tail (~24 per resident warp), windows small enough that the posting ranges all queries of the
+    // batch read inside one window stay in L2 (~192k docs), bounded by the merge capacity.
+    const int64_t resident = (int64_t)h->num_sms * (wide ? 1 : 2) * kSwWarps;
+    S = std::max<int64_t>((24 * resident + nq - 1) / nq, (h->N + 196607) / 196608);
+    if (tuning().bm25_spans > 0) S = tuning().bm25_spans;
+    S = std::max<int64_t>(1, std::min<int64_t>({S, nsl, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
+    if ((uint64_t)nq * (uint64_t)S >= 0xFFFF0000ull) return set_err(HR_ERR_INVALID, "bm25: too many (query, window) jobs");
+  } else {
+    // spans per query: ~8 waves of CTAs over the machine (kBsCtasPerSm resident per SM), bounded by the merge
+    // capacity; a CTA wants at least one slice per warp
+    const int waves = tuning().bm25_waves;
+    S = ((int64_t)waves * kBsCtasPerSm * h->num_sms + nq - 1) / nq;
+    S = std::max<int64_t>(1, std::min<int64_t>({S, (nsl + kBsWarps - 1) / kBsWarps, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
+  }
+  spc = (int)((nsl + S - 1) / S);
   S = (nsl + spc - 1) / spc;
   HR_TRY(h->plan_nt.ensure((size_t)nq * 4));
   HR_TRY(h->plan_start.ensure(nterm_slots * 8));
@@ -1197,11 +1425,15 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   HR_TRY(h->tau.ensure((size_t)nq * 8));
   HR_TRY(h->keys.ensure((size_t)nq * S * k * 8));
   HR_TRY(h->ns.ensure((size_t)nq * S * 4));
+  HR_TRY(h->jobctr.ensure(4));
   HR_CUDA(cudaMemsetAsync(h->tau.p, 0, (size_t)nq * 8, st));
+  HR_TRY(h->plan_err.ensure(4));
+  HR_CUDA(cudaMemsetAsync(h->plan_err.p, 0, 4, st));
   bm25_plan_terms_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(
-      h->indptr, h->idf, h->V, qi_dev, qt_dev, (int)nq, h->plan_nt.as<int>(), h->plan_start.as<int64_t>(),
-      h->plan_len.as<uint32_t>(), h->plan_wgt.as<float>(), touched_dev);
+      h->indptr, h->pstart, h->idf, h->V, qi_dev, qt_dev, (int)nq, h->plan_nt.as<int>(), h->plan_start.as<int64_t>(),
+      h->plan_len.as<uint32_t>(), h->plan_wgt.as<float>(), touched_dev, h->plan_err.as<int>());
   HR_LAUNCHED();
+  HR_CUDA(cudaMemcpyAsync(h->h_plan_err, h->plan_err.p, 4, cudaMemcpyDeviceToHost, st));
   {
     // coarse boundaries (every kBsCoarse slices) by a search over the whole list, then every slice boundary
     // inside its bracketing coarse pair
@@ -1218,7 +1450,42 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
                                                    h->plan_cur.as<uint32_t>());
     HR_LAUNCHED();
   }
+  if (sweep) {
+    HR_CUDA(cudaMemsetAsync(h->jobctr.p, 0, 4, st));
+    const int smem = kSwWarps * sw_warp_bytes(slice_docs, kcp);
+    const int64_t njobs = nq * S;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->num_sms * (wide ? 1 : 2), (njobs + kSwWarps - 1) / kSwWarps));
+    auto launch = [&](auto kern) -> int {
+      HR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      kern<<<grid, kSwThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
+                                           h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
+                                           h->plan_cur.as<uint32_t>(), nsl, spc, (int)S, (int)nq, k, kcp,
+                                           h->keys.as<uint64_t>(), h->ns.as<int>(), h->tau.as<unsigned long long>(),
+                                           h->jobctr.as<unsigned int>());
+      HR_LAUNCHED();
+      return HR_OK;
+    };
+    const int batch = tuning().bm25_batch;
+    if (slice_docs == kSwSliceA) {
+      if (batch == 2) HR_TRY(launch(bm25_sweep_kernel<kSwSliceA, 2>));
+      else HR_TRY(launch(bm25_sweep_kernel<kSwSliceA, 3>));
+    } else if (slice_docs == kSwSliceB) {
+      if (batch == 2) HR_TRY(launch(bm25_sweep_kernel<kSwSliceB, 2>));
+      else HR_TRY(launch(bm25_sweep_kernel<kSwSliceB, 3>));
+    } else if (slice_docs == kSwSliceWideA) {
+      if (batch == 2) HR_TRY(launch(bm25_sweep_kernel<kSwSliceWideA, 3>));
+      else HR_TRY(launch(bm25_sweep_kernel<kSwSliceWideA, 4>));
+    } else {
+      if (batch == 2) HR_TRY(launch(bm25_sweep_kernel<kSwSliceWideB, 3>));
+      else HR_TRY(launch(bm25_sweep_kernel<kSwSliceWideB, 4>));
+    }
+    bm25_sweep_merge_kernel<<<(unsigned)nq, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), (int)S, k, k,
+                                                          h->tau.as<unsigned long long>(), h->id_base, S_dev, I_dev);
+    HR_LAUNCHED();
+    return HR_OK;
+  }
   {
+    const int smem = bs_smem_bytes(kcp);
     dim3 grid((unsigned)nq, (unsigned)S);
     auto launch = [&](auto kern) -> int {
       HR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1238,6 +1505,20 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   return HR_OK;
 }
 
+static int bm25_check_plan(hr_bm25* h) {   // after a synchronisation of the stream bm25_search_dev ran on
+  if (*h->h_plan_err) {
+    *h->h_plan_err = 0;
+    return set_err(HR_ERR_INVALID, "a query has more than 64 distinct scorable terms");
+  }
+  return HR_OK;
+}
+static int check_query_csr_host(const int32_t* q_indptr, int64_t nq) {
+  if (q_indptr[0] < 0) return set_err(HR_ERR_INVALID, "q_indptr must start at a non-negative offset");
+  for (int64_t i = 0; i < nq; ++i)
+    if (q_indptr[i + 1] < q_indptr[i]) return set_err(HR_ERR_INVALID, "q_indptr must be non-decreasing");
+  return HR_OK;
+}
+
 extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t* q_terms, int64_t nq,
                               int64_t n_terms, int k, float* S, int64_t* I, int io_on_device, void* stream,
                               int64_t* postings_touched) {
@@ -1247,19 +1528,16 @@ extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t
   if (nq == 0) return HR_OK;
   if (!q_indptr || !S || !I) return set_err(HR_ERR_INVALID, "null argument");
   HR_DEVICE(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
   cudaStream_t st = (cudaStream_t)stream;
   HR_TRY(h->touched.ensure(8));
   HR_CUDA(cudaMemsetAsync(h->touched.p, 0, 8, st));
   if (io_on_device) {
     HR_TRY(bm25_search_dev(h, q_indptr, q_terms, nq, n_terms, k, S, I, st, h->touched.as<unsigned long long>()));
   } else {
+    HR_TRY(check_query_csr_host(q_indptr, nq));
     const int64_t nterms = q_indptr[nq];
     if (n_terms >= 0 && n_terms < nterms) return set_err(HR_ERR_INVALID, "n_terms is smaller than q_indptr[nq]");
-    for (int64_t i = 0; i < nq; ++i) {
-      if (q_indptr[i + 1] < q_indptr[i]) return set_err(HR_ERR_INVALID, "q_indptr must be non-decreasing");
-      if (q_indptr[i + 1] - q_indptr[i] > kBmMaxTerms)
-        return set_err(HR_ERR_INVALID, "a query has more than 64 terms");
-    }
     HR_TRY(h->io_qi.ensure((size_t)(nq + 1) * 4));
     HR_TRY(h->io_qt.ensure((size_t)std::max<int64_t>(nterms, 1) * 4));
     HR_TRY(h->io_S.ensure((size_t)nq * k * 4));
@@ -1275,7 +1553,7 @@ extern "C" int hr_bm25_search(hr_bm25* h, const int32_t* q_indptr, const int32_t
   HR_CUDA(cudaMemcpyAsync(&t, h->touched.p, 8, cudaMemcpyDeviceToHost, st));
   HR_CUDA(cudaStreamSynchronize(st));
   if (postings_touched) *postings_touched = (int64_t)t;
-  return HR_OK;
+  return bm25_check_plan(h);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1312,40 +1590,22 @@ extern "C" int hr_fuse(const float* dense_D, const int64_t* dense_I, const float
 // -------------------------------------------------------------------------------------------------
 // row-sharded retrieval: local candidates of one shard, and the merge + fusion of the gathered shards
 // -------------------------------------------------------------------------------------------------
-extern "C" int hr_candidates(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
-                             const int32_t* q_terms, int64_t nq, int64_t n_terms, int kc, float* D, int64_t* I,
-                             float* S, int64_t* J, void* stream) {
-  if (!ix) return set_err(HR_ERR_INVALID, "null index");
-  if (nq < 0 || kc <= 0 || kc > kBmMaxK) return set_err(HR_ERR_INVALID, "candidates: kc must be in [1, 128]");
-  if (nq == 0) return HR_OK;
-  if (!q || !D || !I || !S || !J) return set_err(HR_ERR_INVALID, "null argument");
-  if (bm && !q_indptr) return set_err(HR_ERR_INVALID, "null query tokens");
-  if (bm && bm->device != ix->device) return set_err(HR_ERR_INVALID, "index and bm25 live on different devices");
-  HR_DEVICE(ix->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  // BM25 first (asynchronous), then the dense search (which synchronises the stream)
+// BM25 then dense for one shard, all enqueued on `st` (no synchronisation): S,J then D,I [nq,kc] on the device
+static int candidates_enqueue(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* qi, const int32_t* qt,
+                              int64_t nq, int64_t n_terms, int kc, float* D, int64_t* I, float* S, int64_t* J,
+                              cudaStream_t st) {
   if (bm) {
-    HR_TRY(bm25_search_dev(bm, q_indptr, q_terms, nq, n_terms, kc, S, J, st, nullptr));
+    HR_TRY(bm25_search_dev(bm, qi, qt, nq, n_terms, kc, S, J, st, nullptr));
   } else {
     fill_pad_kernel<<<(int)std::min<int64_t>((nq * kc + 255) / 256, 1024), 256, 0, st>>>(S, J, nq * kc, 0.f);
     HR_LAUNCHED();
   }
-  return index_search_dev(ix, q, nq, kc, D, I, st);
+  return index_search_enqueue(ix, q, nq, kc, D, I, st);
 }
 
-extern "C" int hr_merge_fuse_lists(hr_index* ix, const float* D, const int64_t* I, const float* S, const int64_t* J,
-                                   int n_lists, int64_t list_stride_bytes, int64_t nq, int kc, int top_k, int mode,
-                                   float w_vec, float w_bm25, float* out_S, int64_t* out_I, void* stream) {
-  if (!ix) return set_err(HR_ERR_INVALID, "null index");
-  if (nq < 0 || kc <= 0 || top_k <= 0 || n_lists <= 0) return set_err(HR_ERR_INVALID, "bad merge_fuse arguments");
-  if (kc > kFuseMaxKc) return set_err(HR_ERR_INVALID, "merge_fuse: candidate depth kc must be <= 256");
-  if ((int64_t)n_lists * kc > kMergeTopkCap) return set_err(HR_ERR_INVALID, "merge_fuse: more than 2048 candidates per query");
-  if (list_stride_bytes % 8 != 0) return set_err(HR_ERR_INVALID, "merge_fuse: list stride must be a multiple of 8 bytes");
-  if (mode != HR_FUSE_WEIGHTED && mode != HR_FUSE_RRF) return set_err(HR_ERR_INVALID, "unknown fusion mode");
-  if (nq == 0) return HR_OK;
-  if (!D || !I || !S || !J || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
-  HR_DEVICE(ix->device);
-  cudaStream_t st = (cudaStream_t)stream;
+static int merge_fuse_enqueue(hr_index* ix, const float* D, const int64_t* I, const float* S, const int64_t* J,
+                              int n_lists, int64_t list_stride_bytes, int64_t nq, int kc, int top_k, int mode,
+                              float w_vec, float w_bm25, float* out_S, int64_t* out_I, cudaStream_t st) {
   const float* dD = D;
   const int64_t* dI = I;
   const float* bS = S;
@@ -1375,29 +1635,201 @@ extern "C" int hr_merge_fuse_lists(hr_index* ix, const float* D, const int64_t* 
   return HR_OK;
 }
 
-// -------------------------------------------------------------------------------------------------
-// whole hot path on one device
-// -------------------------------------------------------------------------------------------------
-
-extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
-                           const int32_t* q_terms, int64_t nq, int64_t n_terms, int top_k, int kc, int mode, float w_vec,
-                           float w_bm25, float* out_S, int64_t* out_I, int io_on_device, void* stream) {
+extern "C" int hr_candidates(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
+                             const int32_t* q_terms, int64_t nq, int64_t n_terms, int kc, float* D, int64_t* I,
+                             float* S, int64_t* J, void* stream) {
   if (!ix) return set_err(HR_ERR_INVALID, "null index");
-  if (nq < 0 || top_k <= 0) return set_err(HR_ERR_INVALID, "bad retrieve arguments");
-  if (kc <= 0) kc = top_k > 50 ? top_k : 50;  // live path depth, rag/query/page_retriever.py:81
-  if (kc < top_k) kc = top_k;
-  if (kc > kBmMaxK) return set_err(HR_ERR_INVALID, "retrieve: candidate depth must be <= 128");
+  if (nq < 0 || kc <= 0 || kc > kBmMaxK) return set_err(HR_ERR_INVALID, "candidates: kc must be in [1, 128]");
   if (nq == 0) return HR_OK;
-  if (!q || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
-  if (bm && (!q_indptr)) return set_err(HR_ERR_INVALID, "null query tokens");
+  if (!q || !D || !I || !S || !J) return set_err(HR_ERR_INVALID, "null argument");
+  if (bm && !q_indptr) return set_err(HR_ERR_INVALID, "null query tokens");
   if (bm && bm->device != ix->device) return set_err(HR_ERR_INVALID, "index and bm25 live on different devices");
   HR_DEVICE(ix->device);
+  std::unique_lock<std::mutex> l1(ix->mu), l2;
+  if (bm) l2 = std::unique_lock<std::mutex>(bm->mu);
   cudaStream_t st = (cudaStream_t)stream;
+  HR_TRY(candidates_enqueue(ix, bm, q, q_indptr, q_terms, nq, n_terms, kc, D, I, S, J, st));
+  HR_CUDA(cudaStreamSynchronize(st));
+  HR_TRY(index_search_finish(ix, st, nullptr));
+  return bm ? bm25_check_plan(bm) : HR_OK;
+}
+
+extern "C" int hr_merge_fuse_lists(hr_index* ix, const float* D, const int64_t* I, const float* S, const int64_t* J,
+                                   int n_lists, int64_t list_stride_bytes, int64_t nq, int kc, int top_k, int mode,
+                                   float w_vec, float w_bm25, float* out_S, int64_t* out_I, void* stream) {
+  if (!ix) return set_err(HR_ERR_INVALID, "null index");
+  if (nq < 0 || kc <= 0 || top_k <= 0 || n_lists <= 0) return set_err(HR_ERR_INVALID, "bad merge_fuse arguments");
+  if (kc > kFuseMaxKc) return set_err(HR_ERR_INVALID, "merge_fuse: candidate depth kc must be <= 256");
+  if ((int64_t)n_lists * kc > kMergeTopkCap) return set_err(HR_ERR_INVALID, "merge_fuse: more than 2048 candidates per query");
+  if (list_stride_bytes % 8 != 0) return set_err(HR_ERR_INVALID, "merge_fuse: list stride must be a multiple of 8 bytes");
+  if (mode != HR_FUSE_WEIGHTED && mode != HR_FUSE_RRF) return set_err(HR_ERR_INVALID, "unknown fusion mode");
+  if (nq == 0) return HR_OK;
+  if (!D || !I || !S || !J || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
+  HR_DEVICE(ix->device);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  return merge_fuse_enqueue(ix, D, I, S, J, n_lists, list_stride_bytes, nq, kc, top_k, mode, w_vec, w_bm25, out_S, out_I,
+                            (cudaStream_t)stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// whole hot path: one device (hr_retrieve) or one row shard per rank with the exchange inside (hr_retrieve_sharded)
+// -------------------------------------------------------------------------------------------------
+// NCCL is bound at run time (dlopen of the library the host process already uses, e.g. torch's), so libhr_b200.so
+// has no link-time NCCL dependency and a world of 1 needs no NCCL at all.
+typedef struct { char internal[128]; } hr_nccl_id;   // = ncclUniqueId (NCCL_UNIQUE_ID_BYTES)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(hr_nccl_id*) = nullptr;
+  int (*CommInitRank)(void**, int, hr_nccl_id, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {getenv("HR_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      void* l = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (!l) continue;
+      api.GetUniqueId = (int (*)(hr_nccl_id*))dlsym(l, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void**, int, hr_nccl_id, int))dlsym(l, "ncclCommInitRank");
+      api.CommDestroy = (int (*)(void*))dlsym(l, "ncclCommDestroy");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(l, "ncclAllGather");
+      api.GetErrorString = (const char* (*)(int))dlsym(l, "ncclGetErrorString");
+      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather) {
+        api.lib = l;
+        return;
+      }
+      dlclose(l);
+    }
+  });
+  return api.lib ? &api : nullptr;
+}
+static int nccl_err(NcclApi* a, int rc, const char* what) {
+  std::string m = std::string(what) + " failed";
+  if (a && a->GetErrorString) m += std::string(": ") + a->GetErrorString(rc);
+  return set_err(HR_ERR_CUDA, m);
+}
+
+struct hr_comm {
+  int rank = 0, world = 1, device = 0;
+  void* nccl = nullptr;        // ncclComm_t (world > 1)
+  DevBuf local, gathered, q, qi, qt, oS, oI, flag;
+  int* h_flag = nullptr;       // pinned: some rank has fallback queries beyond the device-driven capacity
+  std::mutex mu;
+};
+
+extern "C" int hr_comm_unique_id(void* out_id_128_bytes) {
+  if (!out_id_128_bytes) return set_err(HR_ERR_INVALID, "null id buffer");
+  NcclApi* a = nccl_api();
+  if (!a) return set_err(HR_ERR_CUDA, "libnccl.so.2 not found (set HR_NCCL_LIB)");
+  hr_nccl_id id;
+  const int rc = a->GetUniqueId(&id);
+  if (rc != 0) return nccl_err(a, rc, "ncclGetUniqueId");
+  memcpy(out_id_128_bytes, &id, sizeof id);
+  return HR_OK;
+}
+
+extern "C" int hr_comm_init(const void* unique_id_128_bytes, int rank, int world, int device, hr_comm** out) {
+  if (!out) return set_err(HR_ERR_INVALID, "null out");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return set_err(HR_ERR_INVALID, "bad rank / world");
+  if ((int64_t)world * 1 > kMergeTopkCap) return set_err(HR_ERR_INVALID, "world too large");
+  int ndev = 0;
+  HR_TRY(hr_device_count(&ndev));
+  if (ndev <= 0) return set_err(HR_ERR_CUDA, "no CUDA device (hr_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(HR_ERR_INVALID, "device ordinal out of range");
+  HR_DEVICE(device);
+  hr_comm* c = new hr_comm();
+  c->rank = rank;
+  c->world = world;
+  c->device = device;
+  if (cudaMallocHost((void**)&c->h_flag, 4) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete c;
+    return set_err(HR_ERR_NOMEM, "pinned allocation failed in hr_comm_init");
+  }
+  *c->h_flag = 0;
+  if (world > 1) {
+    if (!unique_id_128_bytes) {
+      hr_comm_destroy(c);
+      return set_err(HR_ERR_INVALID, "null unique id");
+    }
+    NcclApi* a = nccl_api();
+    if (!a) {
+      hr_comm_destroy(c);
+      return set_err(HR_ERR_CUDA, "libnccl.so.2 not found (set HR_NCCL_LIB)");
+    }
+    hr_nccl_id id;
+    memcpy(&id, unique_id_128_bytes, sizeof id);
+    const int rc = a->CommInitRank(&c->nccl, world, id, rank);
+    if (rc != 0) {
+      c->nccl = nullptr;
+      hr_comm_destroy(c);
+      return nccl_err(a, rc, "ncclCommInitRank");
+    }
+  }
+  *out = c;
+  return HR_OK;
+}
+
+extern "C" int hr_comm_destroy(hr_comm* c) {
+  if (!c) return HR_OK;
+  DeviceGuard g(c->device);
+  if (c->nccl) {
+    NcclApi* a = nccl_api();
+    if (a) a->CommDestroy(c->nccl);
+  }
+  if (c->h_flag) cudaFreeHost(c->h_flag);
+  DevBuf* bufs[] = {&c->local, &c->gathered, &c->q, &c->qi, &c->qt, &c->oS, &c->oI, &c->flag};
+  for (DevBuf* b : bufs) b->release();
+  delete c;
+  return HR_OK;
+}
+extern "C" int hr_comm_rank(const hr_comm* c) { return c ? c->rank : -1; }
+extern "C" int hr_comm_world(const hr_comm* c) { return c ? c->world : -1; }
+
+// trailer of a rank's packed block: [0] = this rank has more fallback queries than the device-driven capacity
+__global__ void shard_trailer_kernel(const int* __restrict__ counters, int cap, int* __restrict__ trailer) {
+  if (threadIdx.x == 0) {
+    trailer[0] = (counters && counters[0] > cap) ? 1 : 0;
+    trailer[1] = 0;
+  }
+}
+__global__ void shard_flag_kernel(const uint8_t* __restrict__ gathered, int64_t block_bytes, int64_t trailer_off,
+                                  int world, int* __restrict__ flag) {
+  if (threadIdx.x == 0) {
+    int f = 0;
+    for (int r = 0; r < world; ++r) f |= *(const int*)(gathered + (size_t)r * block_bytes + trailer_off);
+    *flag = f;
+  }
+}
+
+static int retrieve_impl(hr_comm* c, hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
+                         const int32_t* q_terms, int64_t nq, int64_t n_terms, int top_k, int kc, int mode, float w_vec,
+                         float w_bm25, float* out_S, int64_t* out_I, int io_on_device, cudaStream_t st) {
+  const int world = c ? c->world : 1;
+  // one packed block per rank: D fp32 | S fp32 | I int64 | J int64 ([nq,kc] each) | trailer (16 bytes)
+  const int64_t n = nq * kc;
+  const int64_t block = 24 * n + 16;
   RetrieveScratch& rs = ix->rs;
-  HR_TRY(rs.dD.ensure((size_t)nq * kc * 4));
-  HR_TRY(rs.dI.ensure((size_t)nq * kc * 8));
-  HR_TRY(rs.bS.ensure((size_t)nq * kc * 4));
-  HR_TRY(rs.bI.ensure((size_t)nq * kc * 8));
+  DevBuf& local = c ? c->local : rs.dD;
+  HR_TRY(local.ensure((size_t)block));
+  uint8_t* lb = local.as<uint8_t>();
+  float* lD = (float*)lb;
+  float* lS = lD + n;
+  int64_t* lI = (int64_t*)(lb + 8 * n);
+  int64_t* lJ = lI + n;
+  int* trailer = (int*)(lb + 24 * n);
+  uint8_t* gb = lb;
+  if (world > 1) {
+    HR_TRY(c->gathered.ensure((size_t)block * world));
+    HR_TRY(c->flag.ensure(4));
+    gb = c->gathered.as<uint8_t>();
+  }
   const float* qd = q;
   const int32_t* qid = q_indptr;
   const int32_t* qtd = q_terms;
@@ -1408,11 +1840,9 @@ extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int3
     HR_CUDA(cudaMemcpyAsync(rs.q.p, q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
     qd = rs.q.as<float>();
     if (bm) {
+      HR_TRY(check_query_csr_host(q_indptr, nq));
       const int64_t nterms = q_indptr[nq];
       n_terms = nterms;
-      for (int64_t i = 0; i < nq; ++i)
-        if (q_indptr[i + 1] < q_indptr[i] || q_indptr[i + 1] - q_indptr[i] > kBmMaxTerms)
-          return set_err(HR_ERR_INVALID, "bad q_indptr (non-monotone, or a query has more than 64 terms)");
       HR_TRY(rs.qi.ensure((size_t)(nq + 1) * 4));
       HR_TRY(rs.qt.ensure((size_t)std::max<int64_t>(nterms, 1) * 4));
       HR_CUDA(cudaMemcpyAsync(rs.qi.p, q_indptr, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -1425,23 +1855,75 @@ extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int3
     oS = rs.oS.as<float>();
     oI = rs.oI.as<int64_t>();
   }
-  // BM25 first (asynchronous), then the dense search (which synchronises), then fusion
-  if (bm) {
-    HR_TRY(bm25_search_dev(bm, qid, qtd, nq, n_terms, kc, rs.bS.as<float>(), rs.bI.as<int64_t>(), st, nullptr));
-  } else {
-    fill_pad_kernel<<<(int)std::min<int64_t>((nq * kc + 255) / 256, 1024), 256, 0, st>>>(
-        rs.bS.as<float>(), rs.bI.as<int64_t>(), nq * kc, 0.f);
-    HR_LAUNCHED();
+  // BM25, dense (decisions on the device), exchange, merge + fusion: one stream, no host round-trip in between
+  HR_TRY(candidates_enqueue(ix, bm, qd, qid, qtd, nq, n_terms, kc, lD, lI, lS, lJ, st));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (world > 1) {
+      NcclApi* a = nccl_api();
+      shard_trailer_kernel<<<1, 32, 0, st>>>(ix->pend ? ix->counters.as<int>() : nullptr, ix->pend_cap, trailer);
+      HR_LAUNCHED();
+      const int rc = a->AllGather(lb, gb, (size_t)block, 1 /* ncclUint8 */, c->nccl, st);
+      if (rc != 0) return nccl_err(a, rc, "ncclAllGather");
+      shard_flag_kernel<<<1, 32, 0, st>>>(gb, block, 24 * n, world, c->flag.as<int>());
+      HR_LAUNCHED();
+      HR_CUDA(cudaMemcpyAsync(c->h_flag, c->flag.p, 4, cudaMemcpyDeviceToHost, st));
+    }
+    HR_TRY(merge_fuse_enqueue(ix, (const float*)gb, (const int64_t*)(gb + 8 * n), (const float*)gb + n,
+                              (const int64_t*)(gb + 8 * n) + n, world, block, nq, kc, top_k, mode, w_vec, w_bm25, oS, oI,
+                              st));
+    if (!io_on_device) {
+      HR_CUDA(cudaMemcpyAsync(out_S, oS, (size_t)nq * top_k * 4, cudaMemcpyDeviceToHost, st));
+      HR_CUDA(cudaMemcpyAsync(out_I, oI, (size_t)nq * top_k * 8, cudaMemcpyDeviceToHost, st));
+    }
+    HR_CUDA(cudaStreamSynchronize(st));
+    bool changed = false;
+    HR_TRY(index_search_finish(ix, st, &changed));
+    // A rank with more fallback queries than the device-driven capacity has now finished them on the host path;
+    // every rank saw the same trailers, so all of them repeat the exchange and the merge (never in the benchmarks).
+    const bool again = world > 1 ? (*c->h_flag != 0) : changed;
+    if (!again) break;
   }
-  HR_TRY(index_search_dev(ix, qd, nq, kc, rs.dD.as<float>(), rs.dI.as<int64_t>(), st));
-  fuse_kernel<<<(unsigned)nq, 256, 0, st>>>(rs.dD.as<float>(), rs.dI.as<int64_t>(), rs.bS.as<float>(),
-                                            rs.bI.as<int64_t>(), nullptr, kc, top_k, ix->metric, mode, w_vec, w_bm25,
-                                            oS, oI);
-  HR_LAUNCHED();
-  if (!io_on_device) {
-    HR_CUDA(cudaMemcpyAsync(out_S, oS, (size_t)nq * top_k * 4, cudaMemcpyDeviceToHost, st));
-    HR_CUDA(cudaMemcpyAsync(out_I, oI, (size_t)nq * top_k * 8, cudaMemcpyDeviceToHost, st));
-  }
-  HR_CUDA(cudaStreamSynchronize(st));
+  return bm ? bm25_check_plan(bm) : HR_OK;
+}
+
+static int retrieve_args(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr, int64_t nq, int top_k,
+                         int& kc, int mode, float* out_S, int64_t* out_I) {
+  if (!ix) return set_err(HR_ERR_INVALID, "null index");
+  if (nq < 0 || top_k <= 0) return set_err(HR_ERR_INVALID, "bad retrieve arguments");
+  if (mode != HR_FUSE_WEIGHTED && mode != HR_FUSE_RRF) return set_err(HR_ERR_INVALID, "unknown fusion mode");
+  if (kc <= 0) kc = top_k > 50 ? top_k : 50;  // live path depth, rag/query/page_retriever.py:81
+  if (kc < top_k) kc = top_k;
+  if (kc > kBmMaxK) return set_err(HR_ERR_INVALID, "retrieve: candidate depth must be <= 128");
+  if (nq > 0 && (!q || !out_S || !out_I)) return set_err(HR_ERR_INVALID, "null argument");
+  if (bm && (!q_indptr)) return set_err(HR_ERR_INVALID, "null query tokens");
+  if (bm && bm->device != ix->device) return set_err(HR_ERR_INVALID, "index and bm25 live on different devices");
   return HR_OK;
+}
+
+extern "C" int hr_retrieve(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
+                           const int32_t* q_terms, int64_t nq, int64_t n_terms, int top_k, int kc, int mode, float w_vec,
+                           float w_bm25, float* out_S, int64_t* out_I, int io_on_device, void* stream) {
+  HR_TRY(retrieve_args(ix, bm, q, q_indptr, nq, top_k, kc, mode, out_S, out_I));
+  if (nq == 0) return HR_OK;
+  HR_DEVICE(ix->device);
+  std::unique_lock<std::mutex> l1(ix->mu), l2;
+  if (bm) l2 = std::unique_lock<std::mutex>(bm->mu);
+  return retrieve_impl(nullptr, ix, bm, q, q_indptr, q_terms, nq, n_terms, top_k, kc, mode, w_vec, w_bm25, out_S, out_I,
+                       io_on_device, (cudaStream_t)stream);
+}
+
+extern "C" int hr_retrieve_sharded(hr_comm* c, hr_index* ix, hr_bm25* bm, const float* q, const int32_t* q_indptr,
+                                   const int32_t* q_terms, int64_t nq, int64_t n_terms, int top_k, int kc, int mode,
+                                   float w_vec, float w_bm25, float* out_S, int64_t* out_I, int io_on_device,
+                                   void* stream) {
+  if (!c) return set_err(HR_ERR_INVALID, "null comm");
+  HR_TRY(retrieve_args(ix, bm, q, q_indptr, nq, top_k, kc, mode, out_S, out_I));
+  if (c->device != ix->device) return set_err(HR_ERR_INVALID, "comm and index live on different devices");
+  if ((int64_t)c->world * kc > kMergeTopkCap) return set_err(HR_ERR_INVALID, "retrieve_sharded: world * kc exceeds 2048");
+  if (nq == 0) return HR_OK;   // every rank must call with the same nq
+  HR_DEVICE(ix->device);
+  std::unique_lock<std::mutex> l0(c->mu), l1(ix->mu), l2;
+  if (bm) l2 = std::unique_lock<std::mutex>(bm->mu);
+  return retrieve_impl(c, ix, bm, q, q_indptr, q_terms, nq, n_terms, top_k, kc, mode, w_vec, w_bm25, out_S, out_I,
+                       io_on_device, (cudaStream_t)stream);
 }

@@ -54,73 +54,118 @@ def gather_candidates(scores, ids, group=None):
             i_all.permute(1, 0, 2).reshape(nq, world * kc).contiguous())
 
 
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (hr_comm_unique_id): rank 0 creates it, every other rank needs a copy."""
+    import ctypes as C
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.lib().hr_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """One rank of a row-sharded corpus: owns the library's NCCL communicator (include/hr_b200.h: hr_comm_*).
+    `unique_id` may be None when world == 1 (no NCCL involved)."""
+
+    def __init__(self, rank: int, world: int, device: int, unique_id: bytes | None = None):
+        import ctypes as C
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().hr_comm_init(unique_id, self.rank, self.world, self.device, C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def from_torch_distributed(cls, device: int, group=None) -> "Comm":
+        """Rendezvous over an initialised torch.distributed group: rank 0's unique id is broadcast."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return cls(0, 1, device)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", device) if on_gpu else "cpu")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(rank, world, device, bytes(t.cpu().numpy().tobytes()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.lib().hr_comm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class ShardedRetriever:
     """Hybrid retrieval over row shards.  `index` / `bm25` hold THIS rank's shard with id_base set
     to the shard's first global row and BM25 built with global statistics.
 
-    One step = hr_candidates (local BM25 + dense top-k_c into one packed buffer: D | S | I | J),
-    ONE all-gather of that buffer (24 * nq * k_c bytes per rank), hr_merge_fuse_lists reading the
-    gathered per-rank blocks in place (rank order == id order, comparator (score, id))."""
+    One step = ONE C-ABI call, hr_retrieve_sharded: local BM25 + dense top-k_c into one packed block
+    (D | S | I | J, 24 bytes per candidate, + a 16-byte trailer), ONE ncclAllGather of that block on the same
+    stream, merge of the gathered per-rank blocks in place (rank order == id order, comparator (score, id))
+    and fusion; nothing waits for the host in between."""
 
     def __init__(self, index, bm25=None, vector_weight: float = 0.7, bm25_weight: float = 0.3,
-                 fusion: str = "weighted", group=None):
+                 fusion: str = "weighted", group=None, comm: Comm | None = None):
         self.index, self.bm25, self.group = index, bm25, group
         self.vector_weight, self.bm25_weight, self.fusion = vector_weight, bm25_weight, fusion
-        self._bufs = {}
+        self.comm = comm if comm is not None else Comm.from_torch_distributed(index.device, group)
 
     @staticmethod
     def _views(buf, n):
-        """(D float32[n], S float32[n], I int64[n], J int64[n]) views of one packed 24n-byte block."""
+        """(D float32[n], S float32[n], I int64[n], J int64[n]) views of one packed block (first 24n bytes)."""
         import torch
         f = buf[:8 * n].view(torch.float32)
         i = buf[8 * n:24 * n].view(torch.int64)
         return f[:n], f[n:2 * n], i[:n], i[n:2 * n]
 
     def retrieve(self, query_embeddings, query_tokens=None, top_k: int = 10, k_c: int | None = None):
-        """query_embeddings: torch CUDA float32 [nq, d] (replicated on every rank).  Returns torch CUDA
-        (scores [nq, top_k], ids [nq, top_k]) — identical on every rank."""
-        import torch
-        import torch.distributed as dist
+        """query_embeddings: float32 [nq, d], torch CUDA (results stay on the device) or numpy (host in / host
+        out), replicated on every rank.  Returns (scores [nq, top_k], ids [nq, top_k]) — identical on every rank."""
         from .retriever import candidate_depth, _MODES
+        from .bm25 import query_csr
         kc = candidate_depth(top_k) if k_c is None else int(k_c)
-        q = query_embeddings.to(torch.float32).contiguous()
-        dev = q.device
-        nq = q.shape[0]
-        if q.dim() != 2 or q.shape[1] != self.index.d:
-            raise AssertionError(f"retrieve: expected [nq, {self.index.d}] embeddings, got {tuple(q.shape)}")
-        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
-        n = nq * kc
-        key = (nq, kc, world)
-        if key not in self._bufs:
-            local = torch.empty(24 * n, dtype=torch.uint8, device=dev)
-            gathered = torch.empty(world * 24 * n, dtype=torch.uint8, device=dev) if world > 1 else local
-            # raw pointers of the four lists of the local block and of rank 0's block of the gathered buffer
-            self._bufs = {key: (local, gathered, [v.data_ptr() for v in self._views(local, n)],
-                                [v.data_ptr() for v in self._views(gathered, n)])}
-        local, gathered, lp, gp = self._bufs[key]
         use_bm = self.bm25 is not None and query_tokens is not None
-        qi = qt = None
-        if use_bm:
-            from .bm25 import query_csr
-            ip, tm = query_csr(query_tokens)
-            if not hasattr(ip, "is_cuda"):
-                ip = torch.from_numpy(np.ascontiguousarray(ip)).to(dev)
-                tm = torch.from_numpy(np.ascontiguousarray(tm)).to(dev)
-            qi, qt = ip.to(torch.int32).contiguous(), tm.to(torch.int32).contiguous()
-            if qi.shape[0] != nq + 1:
-                raise AssertionError("retrieve: query_tokens and query_embeddings disagree on nq")
         L = _lib.lib()
         st = _lib.current_stream_ptr(self.index.device)
-        # outputs first: hr_candidates returns after a stream synchronisation, nothing but the all-gather and the
-        # merge launch should stand between that point and the GPU's next kernel
-        oS = torch.empty((nq, top_k), dtype=torch.float32, device=dev)
-        oI = torch.empty((nq, top_k), dtype=torch.int64, device=dev)
-        _lib.check(L.hr_candidates(self.index._h, self.bm25._h if use_bm else None, q.data_ptr(),
-                                   qi.data_ptr() if use_bm else None, qt.data_ptr() if use_bm else None, nq,
-                                   int(qt.numel()) if use_bm else 0, kc, lp[0], lp[2], lp[1], lp[3], st))
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, local, group=self.group)
-        _lib.check(L.hr_merge_fuse_lists(self.index._h, gp[0], gp[2], gp[1], gp[3], world, 24 * n, nq, kc, top_k,
-                                         _MODES[self.fusion], self.vector_weight, self.bm25_weight, oS.data_ptr(),
-                                         oI.data_ptr(), st))
+        on_dev = type(query_embeddings).__module__.startswith("torch") and getattr(query_embeddings, "is_cuda", False)
+        if on_dev:
+            import torch
+            q = query_embeddings.to(torch.float32).contiguous()
+            if q.dim() != 2 or q.shape[1] != self.index.d:
+                raise AssertionError(f"retrieve: expected [nq, {self.index.d}] embeddings, got {tuple(q.shape)}")
+            nq = q.shape[0]
+            qi = qt = None
+            if use_bm:
+                ip, tm = query_csr(query_tokens)
+                if not hasattr(ip, "is_cuda"):
+                    ip = torch.from_numpy(np.ascontiguousarray(ip)).to(q.device)
+                    tm = torch.from_numpy(np.ascontiguousarray(tm)).to(q.device)
+                qi, qt = ip.to(torch.int32).contiguous(), tm.to(torch.int32).contiguous()
+                if qi.shape[0] != nq + 1:
+                    raise AssertionError("retrieve: query_tokens and query_embeddings disagree on nq")
+            oS = torch.empty((nq, top_k), dtype=torch.float32, device=q.device)
+            oI = torch.empty((nq, top_k), dtype=torch.int64, device=q.device)
+            _lib.check(L.hr_retrieve_sharded(self.comm._h, self.index._h, self.bm25._h if use_bm else None,
+                                             q.data_ptr(), qi.data_ptr() if use_bm else None,
+                                             qt.data_ptr() if use_bm else None, nq, int(qt.numel()) if use_bm else 0,
+                                             top_k, kc, _MODES[self.fusion], self.vector_weight, self.bm25_weight,
+                                             oS.data_ptr(), oI.data_ptr(), 1, st))
+            return oS, oI
+        q = np.ascontiguousarray(query_embeddings, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.index.d:
+            raise AssertionError(f"retrieve: expected [nq, {self.index.d}] embeddings, got {q.shape}")
+        nq = q.shape[0]
+        qi = qt = None
+        if use_bm:
+            qi, qt = query_csr(query_tokens)
+            if len(qi) != nq + 1:
+                raise AssertionError("retrieve: query_tokens and query_embeddings disagree on nq")
+        oS = np.empty((nq, top_k), dtype=np.float32)
+        oI = np.empty((nq, top_k), dtype=np.int64)
+        _lib.check(L.hr_retrieve_sharded(self.comm._h, self.index._h, self.bm25._h if use_bm else None, q.ctypes.data,
+                                         qi.ctypes.data if use_bm else None, qt.ctypes.data if use_bm else None, nq,
+                                         int(qt.size) if use_bm else 0, top_k, kc, _MODES[self.fusion],
+                                         self.vector_weight, self.bm25_weight, oS.ctypes.data, oI.ctypes.data, 0, st))
         return oS, oI

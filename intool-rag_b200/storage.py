@@ -242,7 +242,9 @@ async def search_hybrid_by_vector(query_vector: List[float], query_text: str, li
     if side is None:
         engine, tokens = HybridRetriever(reader.index, None), None
     else:
-        engine, tokens = HybridRetriever(reader.index, side[0]), [side[1].encode(query_text or "")]
+        from .bm25 import cap_query_terms
+        # a long query text keeps its first 64 distinct in-vocabulary words (the library rejects more)
+        engine, tokens = HybridRetriever(reader.index, side[0]), [cap_query_terms(side[1].encode(query_text or ""))]
     scores, ids = engine.retrieve(q, tokens, top_k=limit, k_c=min(128, max(limit, config.CANDIDATE_DEPTH)))
     chunks = _load_chunk_list(storage_dir, doc_id)
     out = []
