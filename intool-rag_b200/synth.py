@@ -146,6 +146,57 @@ def sparse_corpus_csr_torch(n_docs: int, vocab: int, device, seed: int = SPARSE_
     return indptr.to(torch.int64), post_doc, tf, torch.cat(dls)
 
 
+def sparse_corpus_csr_chunked(n_docs: int, vocab: int, device, seed: int = SPARSE_SEED, mean_len: float = 128.0,
+                              chunk_docs: int = 1 << 20):
+    """Same distributions as sparse_corpus_csr_torch, built without a global sort (BASELINE configs[3]: 50M
+    chunks, 1M-term vocabulary, ~5e9 postings): two passes over doc chunks, every chunk regenerated from its own
+    seed.  Pass 1 counts df per term -> indptr; pass 2 scatters each chunk's (term, doc, tf) triples, already
+    sorted by (term, doc), behind the postings earlier chunks wrote for the same term.  Peak memory = the
+    CSR itself + one chunk.  Returns (indptr int64[V+1], post_doc int32[nnz], post_tf int32[nnz], doc_len int32[n])."""
+    import torch
+    p = 1.0 / torch.arange(1, vocab + 1, dtype=torch.float64, device=device)
+    cdf = torch.cumsum(p / p.sum(), 0)
+
+    def chunk(ci: int, d0: int, nd: int):
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 1000003 + ci)
+        z = torch.randn(nd, generator=g, device=device)
+        dl = torch.clamp(torch.round(torch.exp(np.log(mean_len) + 0.4 * z)), 16, 512).to(torch.int64)
+        total = int(dl.sum().item())
+        u = torch.rand(total, generator=g, device=device, dtype=torch.float64)
+        t = torch.clamp(torch.searchsorted(cdf, u), max=vocab - 1)
+        del u
+        dd = torch.repeat_interleave(torch.arange(nd, device=device, dtype=torch.int64), dl)
+        uk, cnt = torch.unique(t * nd + dd, return_counts=True)       # sorted by (term, local doc)
+        del t, dd
+        return uk // nd, (uk % nd + d0).to(torch.int32), cnt.to(torch.int32), dl.to(torch.int32)
+
+    spans = [(ci, d0, min(chunk_docs, n_docs - d0)) for ci, d0 in enumerate(range(0, n_docs, chunk_docs))]
+    df = torch.zeros(vocab, dtype=torch.int64, device=device)
+    dls = []
+    for ci, d0, nd in spans:
+        terms, _, _, dl = chunk(ci, d0, nd)
+        df += torch.bincount(terms, minlength=vocab)
+        dls.append(dl)
+        del terms
+    indptr = torch.zeros(vocab + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(df, 0)
+    nnz = int(indptr[-1].item())
+    post_doc = torch.empty(nnz, dtype=torch.int32, device=device)
+    post_tf = torch.empty(nnz, dtype=torch.int32, device=device)
+    fill = indptr[:-1].clone()
+    for ci, d0, nd in spans:
+        terms, docs, cnt, _ = chunk(ci, d0, nd)
+        per_term = torch.bincount(terms, minlength=vocab)
+        first = torch.cumsum(per_term, 0) - per_term                 # first triple of each term in this chunk
+        pos = fill[terms] + (torch.arange(terms.numel(), device=device, dtype=torch.int64) - first[terms])
+        post_doc[pos] = docs
+        post_tf[pos] = cnt
+        fill += per_term
+        del terms, docs, cnt, per_term, first, pos
+    return indptr, post_doc, post_tf, torch.cat(dls)
+
+
 def sparse_queries_csr(nq: int, vocab: int, seed: int = SPARSE_SEED + 1, stop: int = STOP_RANKS):
     from .bm25 import query_csr
     return query_csr(sparse_queries_np(nq, vocab, seed, stop))

@@ -167,3 +167,62 @@ def test_synthetic_small_golden_is_reproducible(golden_dir):
     c = bm25.BM25Corpus.from_token_matrix(t, dd, dl, V)
     fs, fi, _ = hybrid.retrieve(ix, c, q, qt, 10, precision="f64")
     assert (fi == z["ip_weighted_I"]).all()
+
+
+def test_fast_cpu_path_equals_the_plain_oracle():
+    """bench.py's CPU arm times oracle/fast.py (sgemm blocks + torch.topk, scipy sparse product): same answers as
+    the plain oracle on a seeded hybrid case (scores exactly / to fp32 rounding, ids outside exact ties)."""
+    from intool_rag_b200 import synth
+    from oracle import bm25, fast, flat, hybrid
+    n, d, V, nq = 6000, 48, 500, 40
+    x = synth.dense_corpus_np(n, d)
+    q = synth.dense_queries_np(x, nq)
+    t, dd, dl = synth.sparse_corpus_np(n, V, mean_len=30.0)
+    qs = synth.sparse_queries_np(nq, V, stop=8)
+    qs[3] = []
+    qs[4] = qs[4] + qs[4][:1]
+    corpus = bm25.BM25Corpus.from_token_matrix(t, dd, dl, V)
+    fbm = fast.FastBM25(corpus)
+    for l2 in (False, True):
+        ix = (flat.IndexFlatL2 if l2 else flat.IndexFlatIP)(d)
+        ix.add(x)
+        D, I = ix.search(q, 50)
+        Df, If = fast.dense_topk(x, q, 50, l2, block=1024)
+        assert np.array_equal(I, If)
+        np.testing.assert_allclose(Df, D, rtol=0, atol=2e-6)
+        S, J = corpus.search(qs, 50)
+        Sf, Jf = fbm.search(qs, 50)
+        np.testing.assert_allclose(Sf, S, rtol=2e-7, atol=0)
+        same = (J == Jf)
+        # ids may differ only inside runs of equal scores (BM25 ties are common; torch.topk orders them freely)
+        assert same.mean() > 0.9 and np.allclose(S[~same], Sf[~same], rtol=2e-7, atol=0)
+        for r in range(nq):
+            assert sorted(J[r][S[r] > S[r, -1]].tolist()) == sorted(Jf[r][Sf[r] > Sf[r, -1]].tolist())
+        fs, fi, _ = hybrid.retrieve(ix, corpus, q, qs, 10)
+        tm = {}
+        gs, gi = fast.retrieve(x, l2, fbm, q, qs, 10, timings=tm)
+        assert (fi == gi).mean() > 0.99
+        np.testing.assert_allclose(gs, fs, rtol=1e-6, atol=1e-7)
+        assert set(tm) == {"dense_s", "bm25_s", "fusion_s"}
+
+
+def test_page_ranking_golden_from_the_reference_run(golden_dir):
+    """tests/golden/ref_wrapper.json:page_ranking was recorded by running the reference's UNMODIFIED
+    PageLevelRetriever.group_chunks_by_page / rank_pages / select_top_pages
+    (/root/reference/rag/query/page_retriever.py:145-236) on the recorded search hits.  A port-free restatement
+    (mean chunk score + min(0.05 n, 0.15), stable sort, top pages) must reproduce it: the scores the engine
+    returns keep their meaning for the page ranking that consumes them."""
+    g = json.load(open(os.path.join(golden_dir, "ref_wrapper.json")))
+    assert len(g["page_ranking"]) == 4
+    for qname, ranking in g["page_ranking"].items():
+        # the ranking was computed from search_faiss_by_vector(limit=20): the first 20 of the recorded limit=50 hits
+        hits = g["search_by_vector"][f"{qname}_l50"][:20]
+        pages = {}
+        for h in hits:                                   # insertion order = order of first appearance
+            pages.setdefault(h["page"], []).append(h["score"])
+        scored = [(page, sum(sc) / len(sc) + min(0.05 * len(sc), 0.15), len(sc)) for page, sc in pages.items()]
+        scored.sort(key=lambda r: -r[1])                 # stable, like the reference's sorted(..., reverse=True)
+        got = scored[:3]
+        assert [r[0] for r in got] == [r[0] for r in ranking], qname
+        assert [r[2] for r in got] == [r[2] for r in ranking], qname
+        np.testing.assert_allclose([r[1] for r in got], [r[1] for r in ranking], rtol=1e-12)
