@@ -74,6 +74,8 @@ typedef struct hr_scan_stats {
 /* ---- library ----------------------------------------------------------------------- */
 const char* hr_last_error(void);
 int hr_version(void);
+/* first 16 hex digits of the sha256 over the library's sources (csrc/Makefile: HASH), compiled in at build time */
+const char* hr_source_hash(void);
 int hr_device_count(int* out);
 /* kernels launched by this library in this process (monotonic; bench.py's gpu_launches). */
 int64_t hr_launch_count(void);
@@ -171,6 +173,18 @@ int hr_fuse(const float* dense_D, const int64_t* dense_I, const float* bm25_S,
             const int64_t* bm25_I, const float* bm25_max, int64_t nq, int kc, int top_k,
             int metric, int mode, float w_vec, float w_bm25, float* out_S, int64_t* out_I,
             int device, void* stream);
+
+/* ---- page-level ranking of a batch of hit lists on the device ---------------------
+ * group_chunks_by_page + rank_pages + select_top_pages of rag/query/page_retriever.py:145-236 for every query
+ * of a batch: the k hits (S, I [nq,k], ids < 0 = padding) are grouped by page_of_row[id - id_base] in order of
+ * first appearance, a page scores mean(hit score) + min(0.05 n, 0.15) in double precision with the reference's
+ * summation order, pages are sorted by score (stable) and the first top_pages are written:
+ * out_page int32[nq,top_pages] (-1 padded), out_score double[nq,top_pages], out_count int32[nq,top_pages].
+ * score_kind 0: S is the hit score (fused score, inner product); 1: S is a squared L2 distance and the hit
+ * score is the wrapper's clamp(1 - d/2, 0, 1) (rag/storage/faiss_index.py:86-88).  Device pointers, k <= 256. */
+int hr_rank_pages(const float* S, const int64_t* I, int64_t nq, int k, int score_kind,
+                  const int32_t* page_of_row, int64_t n_rows, int64_t id_base, int top_pages,
+                  int32_t* out_page, double* out_score, int32_t* out_count, int device, void* stream);
 
 /* ---- row sharding: a rank's local candidates, then merge + fusion of all ranks' ------
  * hr_candidates: dense top-kc (D,I) and BM25 top-kc (S,J) of THIS shard with global ids (id_base),

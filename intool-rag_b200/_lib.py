@@ -33,6 +33,7 @@ _p = C.c_void_p
 SYMBOLS = {
     "hr_last_error": (C.c_char_p, []),
     "hr_version": (C.c_int, []),
+    "hr_source_hash": (C.c_char_p, []),
     "hr_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "hr_launch_count": (C.c_int64, []),
     "hr_set_option": (C.c_int, [C.c_char_p, C.c_int]),
@@ -68,6 +69,8 @@ SYMBOLS = {
     "hr_merge_topk": (C.c_int, [_p, _p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _p, _p, C.c_int, _p]),
     "hr_fuse": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                           C.c_float, _p, _p, C.c_int, _p]),
+    "hr_rank_pages": (C.c_int, [_p, _p, C.c_int64, C.c_int, C.c_int, _p, C.c_int64, C.c_int64, C.c_int, _p, _p, _p,
+                                C.c_int, _p]),
     "hr_candidates": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int, _p, _p, _p, _p, _p]),
     "hr_merge_fuse_lists": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_float, _p, _p, _p]),
@@ -100,6 +103,24 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+SOURCE_FILES = ["hr_api.cu", "common.cuh", "dense_exact.cuh", "dense_scan_tc.cuh", "bm25.cuh", "bm25_sweep.cuh",
+                "bm25_build.cuh", "fuse.cuh", os.path.join("..", "..", "include", "hr_b200.h")]
+
+
+def tree_source_hash() -> str:
+    """sha256 over the library's sources in the Makefile's order (csrc/Makefile: HASH), first 16 hex digits."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in SOURCE_FILES:
+        with open(os.path.join(_HERE, "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def built_source_hash() -> str:
+    return lib().hr_source_hash().decode()
 
 
 def last_error() -> str:

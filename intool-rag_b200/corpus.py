@@ -16,8 +16,9 @@ query (:175, /root/reference/rag/storage/file_storage.py:139-166).  Here:
   a global term's list is the concatenation of the per-document lists.  idf / avgdl come from the whole
   corpus (every file's df and doc_len), also on a rank that holds only a shard.
 * ``ChunkStore``: per chunk a (file, byte offset, byte length) triple into the reference's own
-  ``{doc_id}_chunks.json`` files; a query reads and parses only its k chunks.  Host memory: 20 bytes per
-  chunk (200 MB for 10M chunks) instead of every chunk as a Python dict (>= 10 GB at 10M chunks).
+  ``{doc_id}_chunks.json`` files plus the chunk's page number; a query reads and parses only its k chunks.
+  Host memory: 20 bytes per chunk (200 MB for 10M chunks) instead of every chunk as a Python dict (>= 10 GB at
+  10M chunks).
 """
 from __future__ import annotations
 
@@ -60,10 +61,11 @@ def doc_id_of(index_path: str) -> str:
 # ---------------------------------------------------------------------------------------------------
 # chunk metadata: fetch k rows, not the corpus
 # ---------------------------------------------------------------------------------------------------
-def _chunk_spans(path: str) -> np.ndarray:
+def _chunk_spans(path: str, with_pages: bool = False):
     """Byte spans [[offset, length], ...] of the elements of the "chunks" array of a ``*_chunks.json`` file, in
     the order ``list({c["chunk_id"]: c for c in chunks}.values())`` would have (the reference's row -> chunk
-    mapping, faiss_index.py:176-181): position of the FIRST occurrence of a chunk_id, content of the LAST."""
+    mapping, faiss_index.py:176-181): position of the FIRST occurrence of a chunk_id, content of the LAST.
+    with_pages: also the chunks' "page" values (int32, 0 when absent: the wrapper's default, faiss_index.py:187)."""
     with open(path, "rb") as f:
         raw = f.read()
     text = raw.decode("utf-8")
@@ -71,11 +73,13 @@ def _chunk_spans(path: str) -> np.ndarray:
     dec = json.JSONDecoder()
     key = text.find('"chunks"')
     if key < 0:
-        return np.zeros((0, 2), np.int64)
+        return (np.zeros((0, 2), np.int64), np.zeros(0, np.int32)) if with_pages else np.zeros((0, 2), np.int64)
     i = text.index("[", key) + 1
+    pages: List[int] = []
     spans: List[List[int]] = []
     pos_of: Dict[str, int] = {}
     n = len(text)
+    char_pos, byte_pos = 0, 0        # a character index whose byte offset is known (non-ASCII files)
     while True:
         while i < n and text[i] in " \t\r\n,":
             i += 1
@@ -85,24 +89,23 @@ def _chunk_spans(path: str) -> np.ndarray:
         if ascii_only:
             off, ln = i, end - i
         else:
-            off = len(text[:i].encode("utf-8")) if not spans else None
+            off = byte_pos + len(text[char_pos:i].encode("utf-8"))
             ln = len(text[i:end].encode("utf-8"))
-            if off is None:   # running byte offset: previous element's end + the separator bytes
-                off = _chunk_spans.cursor + len(text[_chunk_spans.char_cursor:i].encode("utf-8"))
-        _chunk_spans.cursor, _chunk_spans.char_cursor = off + ln, end
+            char_pos, byte_pos = end, off + ln
         cid = obj.get("chunk_id") if isinstance(obj, dict) else None
+        page = obj.get("page", 0) if isinstance(obj, dict) else 0
+        page = int(page) if isinstance(page, (int, float)) else 0
         if cid is not None and cid in pos_of:
             spans[pos_of[cid]] = [off, ln]
+            pages[pos_of[cid]] = page
         else:
             if cid is not None:
                 pos_of[cid] = len(spans)
             spans.append([off, ln])
+            pages.append(page)
         i = end
-    return np.asarray(spans, np.int64).reshape(-1, 2)
-
-
-_chunk_spans.cursor = 0
-_chunk_spans.char_cursor = 0
+    out = np.asarray(spans, np.int64).reshape(-1, 2)
+    return (out, np.asarray(pages, np.int32)) if with_pages else out
 
 
 class ChunkStore:
@@ -110,11 +113,14 @@ class ChunkStore:
 
     def __init__(self, chunk_paths: Sequence[str], rows_per_doc: Sequence[int]):
         self.paths = [str(p) for p in chunk_paths]
-        files, offs, lens = [], [], []
+        files, offs, lens, pages = [], [], [], []
         self.row0 = np.zeros(len(self.paths) + 1, np.int64)
         for fi, (p, n_rows) in enumerate(zip(self.paths, rows_per_doc)):
-            spans = _chunk_spans(p) if os.path.exists(p) else np.zeros((0, 2), np.int64)
+            spans, pg = _chunk_spans(p, True) if os.path.exists(p) else (np.zeros((0, 2), np.int64), np.zeros(0, np.int32))
             n = int(n_rows)
+            pr = np.zeros(n, np.int32)
+            pr[:min(n, len(pg))] = pg[:n]
+            pages.append(pr)
             o = np.full(n, -1, np.int64)           # rows without a chunk (shorter JSON) resolve to None
             ln = np.zeros(n, np.int32)
             m = min(n, len(spans))
@@ -126,6 +132,7 @@ class ChunkStore:
         self.file_of = np.concatenate(files) if files else np.zeros(0, np.int32)
         self.offset = np.concatenate(offs) if offs else np.zeros(0, np.int64)
         self.length = np.concatenate(lens) if lens else np.zeros(0, np.int32)
+        self.page_of = np.concatenate(pages) if pages else np.zeros(0, np.int32)   # row -> page (device page ranking)
         self._maps: Dict[int, mmap.mmap] = {}
 
     def __len__(self) -> int:
@@ -133,11 +140,14 @@ class ChunkStore:
 
     @property
     def table_bytes(self) -> int:
-        return int(self.file_of.nbytes + self.offset.nbytes + self.length.nbytes)
+        return int(self.file_of.nbytes + self.offset.nbytes + self.length.nbytes + self.page_of.nbytes)
 
     def _map(self, fi: int) -> mmap.mmap:
         m = self._maps.get(fi)
         if m is None:
+            if len(self._maps) >= 256:               # bounded number of open mappings (thousands of documents)
+                old = next(iter(self._maps))
+                self._maps.pop(old).close()
             with open(self.paths[fi], "rb") as f:
                 m = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
             self._maps[fi] = m

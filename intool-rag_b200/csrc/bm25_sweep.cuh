@@ -19,7 +19,9 @@
 //    [g spj, (g+1) spj) of one query, alone (no block barrier, no atomics on accumulators).  Jobs are drawn
 //    from a global counter in window-major order, so at any time all resident warps work on the same one or
 //    two doc windows of different queries: the posting ranges heavy terms share across queries are read from
-//    HBM once and hit L2 afterwards.  Thresholds travel between the windows of a query through tau_g.
+//    HBM once and hit L2 afterwards.  At the end of a job the warp merges its candidates into the query's
+//    running top-k list in global memory (sorted, one lock per query); the list's last key is the exact
+//    k-th best of all windows scored so far and becomes the threshold (tau_g) of the query's later windows.
 //  * Candidate selection is the round-1 scheme: a doc whose running score reaches the threshold goes to a
 //    small hot list; at the end of the slice only the listed docs become candidate keys.
 #pragma once
@@ -196,15 +198,16 @@ __device__ __forceinline__ void sw_sweep_terms(int lane, int64_t pstart, float w
   }
 }
 
-// out_keys [nq][S][kc] (unsorted), out_n [nq][S]; job j = (window j / nq, query j % nq).
+// use_lock: glist [nq][kc] (sorted best first), gcount [nq], glock [nq]; otherwise glist [nq][S][kc] (unsorted
+// slots), gcount [nq][S].  Job j = (window j / nq, query j % nq).
 template <int SLICE, int kSwBatch>
 __global__ void __launch_bounds__(kSwThreads, (SLICE <= kSwSliceA ? 2 : 1))
 bm25_sweep_kernel(const int32_t* __restrict__ post_doc, const float* __restrict__ post_imp,
                   const int32_t* __restrict__ q_indptr, const int* __restrict__ plan_nt,
                   const int64_t* __restrict__ plan_start, const float* __restrict__ plan_wgt,
                   const uint32_t* __restrict__ plan_cur, int64_t nsl, int spj, int S, int nq, int kc, int kcp,
-                  uint64_t* __restrict__ out_keys, int* __restrict__ out_n, unsigned long long* __restrict__ tau_g,
-                  unsigned int* __restrict__ job_counter) {
+                  uint64_t* glist, int* gcount, int* glock, unsigned long long* __restrict__ tau_g,
+                  unsigned int* __restrict__ job_counter, int use_lock) {
   static_assert(SLICE % 128 == 0 && SLICE <= 65536, "hot list entries are 16-bit doc offsets");
   extern __shared__ __align__(16) uint8_t swm[];
   const int lane = threadIdx.x & 31;
@@ -231,9 +234,8 @@ bm25_sweep_kernel(const int32_t* __restrict__ post_doc, const float* __restrict_
     const int nt = plan_nt[q];
     const int64_t s_begin = (int64_t)g * spj;
     const int64_t s_end = min(nsl, s_begin + spj);
-    uint64_t* o = out_keys + ((size_t)q * S + g) * kc;
     if (nt == 0 || s_begin >= s_end) {
-      if (lane == 0) out_n[(size_t)q * S + g] = 0;
+      if (!use_lock && lane == 0) gcount[(size_t)q * S + g] = 0;
       continue;
     }
     const int qa = q_indptr[q];
@@ -377,22 +379,60 @@ bm25_sweep_kernel(const int32_t* __restrict__ post_doc, const float* __restrict_
       c0 = c1;
       c1 = nxt;
     }
-    // ---- end of job: at most kc keys leave the warp ----
+    // ---- end of job ----
     __syncwarp();
-    if (cbn > kc) {
-      for (int i = cbn + lane; i < cbcap; i += 32) cb[i] = 0;
-      warp_bitonic_desc(cb, cbcap, lane);
-      cbn = kc;
-      if (lane == 0 && cb[kc - 1] > tau) atomicMax(tau_gq, cb[kc - 1]);
+    if (!use_lock) {
+      // small batches (few queries, many simultaneous jobs per query): the job's best kc keys go to its own slot
+      // glist[q][g][kc], gcount[q][g]; bm25_sweep_merge_kernel merges the slots of a query
+      if (cbn > kc) {
+        for (int i = cbn + lane; i < cbcap; i += 32) cb[i] = 0;
+        warp_bitonic_desc(cb, cbcap, lane);
+        cbn = kc;
+        if (lane == 0 && cb[kc - 1] > tau) atomicMax(tau_gq, cb[kc - 1]);
+      }
+      uint64_t* o = glist + ((size_t)q * S + g) * kc;
+      for (int j = lane; j < cbn; j += 32) o[j] = cb[j];
+      if (lane == 0) gcount[(size_t)q * S + g] = cbn;
+      __syncwarp();
+      continue;
     }
-    for (int j = lane; j < cbn; j += 32) o[j] = cb[j];
-    if (lane == 0) out_n[(size_t)q * S + g] = cbn;
-    __syncwarp();
+    // Large batches: merge the warp's candidates into the query's running top-kc (global, sorted, guarded by a
+    // per-query lock; at most a few jobs of one query run at the same time).  Its kc-th key is the exact kc-th
+    // best of every window scored so far: the threshold the later windows of this query start from.  Most warm
+    // jobs have nothing to merge.
+    if (cbn > 0) {   // warp-uniform
+      if (cbn > kcp) {   // make room for the global list
+        for (int i = cbn + lane; i < cbcap; i += 32) cb[i] = 0;
+        warp_bitonic_desc(cb, cbcap, lane);
+        cbn = min(cbn, kc);
+      }
+      uint64_t* gl = glist + (size_t)q * kc;
+      if (lane == 0) {
+        while (atomicCAS(glock + q, 0, 1) != 0) __nanosleep(100);
+        __threadfence();
+      }
+      __syncwarp();
+      const int gn = *((volatile int*)(gcount + q));
+      for (int i = lane; i < gn; i += 32) cb[cbn + i] = __ldcg(reinterpret_cast<const unsigned long long*>(gl + i));
+      const int total = cbn + gn;
+      for (int i = total + lane; i < cbcap; i += 32) cb[i] = 0;
+      warp_bitonic_desc(cb, cbcap, lane);
+      const int m = min(total, kc);
+      for (int i = lane; i < m; i += 32) __stcg(reinterpret_cast<unsigned long long*>(gl + i), cb[i]);
+      __syncwarp();
+      if (lane == 0) {
+        *((volatile int*)(gcount + q)) = m;
+        if (m == kc) atomicMax(tau_gq, cb[kc - 1]);
+        __threadfence();
+        atomicExch(glock + q, 0);
+      }
+      __syncwarp();
+    }
   }
 }
 
-// merge the S unsorted lists of a query: keep keys >= the query's final threshold (a lower bound of the
-// kc-th best key, so nothing that belongs to the top k is dropped), sort, write S_out / I_out [nq][k]
+// small batches: merge the S unsorted slots of a query: keep keys >= the query's final threshold (a lower bound
+// of the kc-th best key, so nothing that belongs to the top k is dropped), sort, write S_out / I_out [nq][k]
 __global__ void __launch_bounds__(256)
 bm25_sweep_merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ ns, int S, int kc, int k,
                         const unsigned long long* __restrict__ tau_g, int64_t id_base, float* __restrict__ So,
@@ -426,6 +466,23 @@ bm25_sweep_merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict
       So[(size_t)q * k + j] = 0.f;
       Io[(size_t)q * k + j] = -1;
     }
+  }
+}
+
+// the query's running top-kc list (sorted best first) -> S_out / I_out [nq][k]
+__global__ void __launch_bounds__(256)
+bm25_sweep_finish_kernel(const uint64_t* __restrict__ glist, const int* __restrict__ gcount, int nq, int kc, int k,
+                         int64_t id_base, float* __restrict__ So, int64_t* __restrict__ Io) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nq * k) return;
+  const int q = (int)(i / k), j = (int)(i - (int64_t)q * k);
+  const uint64_t key = (j < gcount[q]) ? glist[(size_t)q * kc + j] : 0ull;
+  if (key) {
+    So[i] = key_score(key);
+    Io[i] = (int64_t)key_row(key) + id_base;
+  } else {
+    So[i] = 0.f;
+    Io[i] = -1;
   }
 }
 

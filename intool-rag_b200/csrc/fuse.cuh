@@ -143,4 +143,68 @@ merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, in
   }
 }
 
+// ---- page-level ranking of a batch of hit lists --------------------------------------
+// What /root/reference/rag/query/page_retriever.py:145-236 does per request on the host, for every query of a
+// batch on the device: group the k hits by page (first appearance order), page score = mean(hit scores) +
+// min(0.05 n, 0.15), stable sort by score descending, first top_pages.  Double precision with the reference's
+// summation order (hits best first), so the values equal the Python floats of the reference bit for bit.
+// score_kind 0: S is the hit score (fused / inner product); 1: S is a squared L2 distance and the hit score is
+// the wrapper's clamp(1 - d/2, 0, 1) (rag/storage/faiss_index.py:86-88).  One block per query.
+constexpr int kPageMaxHits = 256;
+__global__ void __launch_bounds__(128)
+page_rank_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, int k, int score_kind,
+                 const int32_t* __restrict__ page_of_row, int64_t n_rows, int64_t id_base, int top_pages,
+                 int32_t* __restrict__ oP, double* __restrict__ oS, int32_t* __restrict__ oC) {
+  __shared__ int pg[kPageMaxHits];
+  __shared__ double sc[kPageMaxHits];
+  __shared__ double ps[kPageMaxHits];
+  __shared__ int pc[kPageMaxHits];     // hits of the page led by entry e, 0 = e is not a page's first hit
+  const int q = blockIdx.x;
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    const int64_t id = I[(size_t)q * k + e];
+    const int64_t row = id - id_base;
+    const bool valid = id >= 0 && row >= 0 && row < n_rows;
+    pg[e] = valid ? page_of_row[row] : 0;
+    double v = (double)S[(size_t)q * k + e];
+    if (score_kind == 1) v = fmax(0.0, fmin(1.0, 1.0 - v / 2.0));
+    sc[e] = v;
+    pc[e] = valid ? -1 : -2;            // -1: valid hit, leader unknown; -2: padding
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    if (pc[e] == -2) continue;
+    bool leader = true;
+    for (int j = 0; j < e; ++j)
+      if (pc[j] != -2 && pg[j] == pg[e]) { leader = false; break; }
+    if (!leader) continue;
+    double sum = 0.0;
+    int n = 0;
+    for (int j = e; j < k; ++j)
+      if (pc[j] != -2 && pg[j] == pg[e]) { sum += sc[j]; ++n; }
+    ps[e] = sum / (double)n + fmin((double)n * 0.05, 0.15);
+    pc[e] = -(n + 2);                   // leaders: -(n + 2) <= -3 until every thread has finished reading pc
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < k; e += blockDim.x) pc[e] = pc[e] <= -3 ? -(pc[e] + 2) : 0;
+  __syncthreads();
+  int npages = 0;
+  for (int j = 0; j < k; ++j) npages += pc[j] > 0;
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    if (pc[e] <= 0) continue;
+    int rank = 0;                        // stable: equal scores keep the order of first appearance
+    for (int j = 0; j < k; ++j)
+      if (pc[j] > 0 && (ps[j] > ps[e] || (ps[j] == ps[e] && j < e))) rank++;
+    if (rank < top_pages) {
+      oP[(size_t)q * top_pages + rank] = pg[e];
+      oS[(size_t)q * top_pages + rank] = ps[e];
+      oC[(size_t)q * top_pages + rank] = pc[e];
+    }
+  }
+  for (int j = npages + threadIdx.x; j < top_pages; j += blockDim.x) {
+    oP[(size_t)q * top_pages + j] = -1;
+    oS[(size_t)q * top_pages + j] = 0.0;
+    oC[(size_t)q * top_pages + j] = 0;
+  }
+}
+
 }  // namespace hr

@@ -210,7 +210,13 @@ static const void* filter_rows(const hr_index* h) { return h->storage == HR_STOR
 static int filter_elem(const hr_index* h) { return filter_is_bf16(h) ? 2 : 4; }
 
 extern "C" const char* hr_last_error(void) { return g_err.c_str(); }
-extern "C" int hr_version(void) { return 100; }
+extern "C" int hr_version(void) { return 200; }
+#ifndef HR_SOURCE_HASH
+#define HR_SOURCE_HASH "unknown"
+#endif
+// tagged so that the hash can also be read from the file without loading it (__graft_entry__.build)
+static const char kSourceHashTag[] = "HR_SOURCE_HASH=" HR_SOURCE_HASH;
+extern "C" const char* hr_source_hash(void) { return kSourceHashTag + 15; }
 extern "C" int64_t hr_launch_count(void) { return (int64_t)g_launches.load(); }
 // Tuning / diagnostic knobs by name (the HR_* environment variables without the prefix, lower case).  Not
 // thread-safe against running searches; meant for benchmarks and tests.
@@ -1398,6 +1404,7 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     return set_err(HR_ERR_INVALID, "bm25: query batch too large for the cursor table (split the batch)");
   int64_t S;   // doc windows (spans) per query
   int spc;     // slices per window
+  bool use_lock = false;
   if (sweep) {
     // jobs = (window, query), one warp each, drawn window-major by the resident warps.  Enough jobs for a
     // balanced tail (~24 per resident warp), windows small enough that the posting ranges all queries of the
@@ -1405,7 +1412,11 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     const int64_t resident = (int64_t)h->num_sms * (wide ? 1 : 2) * kSwWarps;
     S = std::max<int64_t>((24 * resident + nq - 1) / nq, (h->N + 196607) / 196608);
     if (tuning().bm25_spans > 0) S = tuning().bm25_spans;
-    S = std::max<int64_t>(1, std::min<int64_t>({S, nsl, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
+    // Large batches keep one running top-k list per query under a lock (few jobs of a query run at the same
+    // time); in a small batch hundreds of jobs of one query finish together and would serialise there, so they
+    // write per-job slots that one merge kernel combines (S * k bounded by its sort buffer).
+    use_lock = nq >= 256;
+    S = std::max<int64_t>(1, std::min<int64_t>({S, nsl, use_lock ? (int64_t)1024 : (int64_t)(kBmMergeCap / k)}));
     if ((uint64_t)nq * (uint64_t)S >= 0xFFFF0000ull) return set_err(HR_ERR_INVALID, "bm25: too many (query, window) jobs");
   } else {
     // spans per query: ~8 waves of CTAs over the machine (kBsCtasPerSm resident per SM), bounded by the merge
@@ -1423,8 +1434,9 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   HR_TRY(h->plan_cur.ensure(cur_bytes));
   HR_TRY(h->plan_coarse.ensure(nterm_slots * (size_t)nbc * 4));
   HR_TRY(h->tau.ensure((size_t)nq * 8));
-  HR_TRY(h->keys.ensure((size_t)nq * S * k * 8));
-  HR_TRY(h->ns.ensure((size_t)nq * S * 4));
+  // sweep: running top-k list per query + count + lock; slot kernel: [nq][S][k] span lists
+  HR_TRY(h->keys.ensure(use_lock ? (size_t)nq * k * 8 : (size_t)nq * S * k * 8));
+  HR_TRY(h->ns.ensure(use_lock ? (size_t)nq * 8 : (size_t)nq * S * 4));
   HR_TRY(h->jobctr.ensure(4));
   HR_CUDA(cudaMemsetAsync(h->tau.p, 0, (size_t)nq * 8, st));
   HR_TRY(h->plan_err.ensure(4));
@@ -1452,6 +1464,7 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   }
   if (sweep) {
     HR_CUDA(cudaMemsetAsync(h->jobctr.p, 0, 4, st));
+    if (use_lock) HR_CUDA(cudaMemsetAsync(h->ns.p, 0, (size_t)nq * 8, st));   // gcount [nq] | glock [nq]
     const int smem = kSwWarps * sw_warp_bytes(slice_docs, kcp);
     const int64_t njobs = nq * S;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->num_sms * (wide ? 1 : 2), (njobs + kSwWarps - 1) / kSwWarps));
@@ -1460,8 +1473,9 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
       kern<<<grid, kSwThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
                                            h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
                                            h->plan_cur.as<uint32_t>(), nsl, spc, (int)S, (int)nq, k, kcp,
-                                           h->keys.as<uint64_t>(), h->ns.as<int>(), h->tau.as<unsigned long long>(),
-                                           h->jobctr.as<unsigned int>());
+                                           h->keys.as<uint64_t>(), h->ns.as<int>(), h->ns.as<int>() + nq,
+                                           h->tau.as<unsigned long long>(), h->jobctr.as<unsigned int>(),
+                                           use_lock ? 1 : 0);
       HR_LAUNCHED();
       return HR_OK;
     };
@@ -1479,8 +1493,12 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
       if (batch == 2) HR_TRY(launch(bm25_sweep_kernel<kSwSliceWideB, 3>));
       else HR_TRY(launch(bm25_sweep_kernel<kSwSliceWideB, 4>));
     }
-    bm25_sweep_merge_kernel<<<(unsigned)nq, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), (int)S, k, k,
-                                                          h->tau.as<unsigned long long>(), h->id_base, S_dev, I_dev);
+    if (use_lock)
+      bm25_sweep_finish_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(),
+                                                                                 (int)nq, k, k, h->id_base, S_dev, I_dev);
+    else
+      bm25_sweep_merge_kernel<<<(unsigned)nq, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), (int)S, k, k,
+                                                            h->tau.as<unsigned long long>(), h->id_base, S_dev, I_dev);
     HR_LAUNCHED();
     return HR_OK;
   }
@@ -1583,6 +1601,22 @@ extern "C" int hr_fuse(const float* dense_D, const int64_t* dense_I, const float
   HR_DEVICE(device);
   fuse_kernel<<<(unsigned)nq, 256, 0, (cudaStream_t)stream>>>(dense_D, dense_I, bm25_S, bm25_I, bm25_max, kc, top_k,
                                                              metric, mode, w_vec, w_bm25, out_S, out_I);
+  HR_LAUNCHED();
+  return HR_OK;
+}
+
+extern "C" int hr_rank_pages(const float* S, const int64_t* I, int64_t nq, int k, int score_kind,
+                             const int32_t* page_of_row, int64_t n_rows, int64_t id_base, int top_pages,
+                             int32_t* out_page, double* out_score, int32_t* out_count, int device, void* stream) {
+  if (nq < 0 || k <= 0 || k > kPageMaxHits) return set_err(HR_ERR_INVALID, "rank_pages: k must be in [1, 256]");
+  if (top_pages <= 0 || top_pages > kPageMaxHits) return set_err(HR_ERR_INVALID, "rank_pages: top_pages must be in [1, 256]");
+  if (score_kind != 0 && score_kind != 1) return set_err(HR_ERR_INVALID, "rank_pages: score_kind must be 0 or 1");
+  if (nq == 0) return HR_OK;
+  if (!S || !I || !page_of_row || !out_page || !out_score || !out_count || n_rows < 0)
+    return set_err(HR_ERR_INVALID, "null argument");
+  HR_DEVICE(device);
+  page_rank_kernel<<<(unsigned)nq, 128, 0, (cudaStream_t)stream>>>(S, I, k, score_kind, page_of_row, n_rows, id_base,
+                                                                  top_pages, out_page, out_score, out_count);
   HR_LAUNCHED();
   return HR_OK;
 }

@@ -11,6 +11,12 @@ file) and `search_hybrid_by_vector` (query vector + query text -> fused hits, sa
 `search_faiss_by_vector`).
 
 Deliberate, documented deviations:
+  * ONE logical corpus: the search functions and `initialize_storage` work on the concatenation of every
+    ``*_faiss.index`` under STORAGE_DIR (sorted by file name; :mod:`.corpus`), not only on the first file the
+    glob returns (faiss_index.py:162-167).  ``STORAGE_MODE=first`` restores the reference's behaviour.  With a
+    single document both modes return the same hits;
+  * hits are enriched by reading only the k chunks they name from ``{doc_id}_chunks.json`` (byte-offset table,
+    20 bytes of host memory per chunk) instead of parsing the whole file into dicts;
   * padded hits (id -1, when limit > ntotal) are dropped instead of silently mapping to the LAST
     chunk through Python's negative indexing (faiss_index.py:180-181);
   * the index cache is keyed by (path, mtime) so a re-ingested document is seen without restart;
@@ -31,6 +37,7 @@ from .config import config
 
 logger = logging.getLogger("intool_rag_b200.storage")
 
+_CORPUS_CACHE: Dict[str, tuple] = {}      # storage_dir -> (signature, Corpus)
 _INDEX_CACHE: Dict[Tuple[str, float], "faiss.Index"] = {}
 _BM25_CACHE: Dict[Tuple[str, float], tuple] = {}
 _CHUNK_CACHE: Dict[Tuple[str, float], List[dict]] = {}
@@ -41,6 +48,34 @@ def _mtime(path: str) -> float:
         return os.path.getmtime(path)
     except OSError:
         return -1.0
+
+
+def storage_mode() -> str:
+    return os.environ.get("STORAGE_MODE", "corpus").lower()
+
+
+def get_corpus(storage_dir: Optional[str] = None, rank: int = 0, world: int = 1):
+    """The logical corpus over `storage_dir` (default STORAGE_DIR), loaded into HBM once and rebuilt when an
+    index file, a BM25 CSR sidecar or the shard (rank, world) changes."""
+    from .corpus import Corpus, csr_sidecar_path, doc_id_of
+    sd = str(storage_dir or os.environ.get("STORAGE_DIR", config.STORAGE_DIR))
+    files = sorted(glob.glob(os.path.join(sd, "*_faiss.index")))
+    sig = (rank, world, os.environ.get("HR_STORAGE", "f32"), config.HYBRID_SEARCH_ENABLED) + tuple(
+        (p, _mtime(p), _mtime(csr_sidecar_path(sd, doc_id_of(p)))) for p in files)
+    hit = _CORPUS_CACHE.get(sd)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    corpus = Corpus(sd, rank=rank, world=world, with_bm25=config.HYBRID_SEARCH_ENABLED)
+    _CORPUS_CACHE[sd] = (sig, corpus)
+    if corpus.docs:
+        logger.info("Loaded corpus: %d documents, %d rows (this shard: rows [%d, %d)), d=%d, chunk table %d bytes",
+                    len(corpus.docs), corpus.ntotal_global, corpus.lo, corpus.hi, corpus.d, corpus.chunks.table_bytes)
+    return corpus
+
+
+def _reference_scores(D) -> List[float]:
+    """clamp(1 - squared_L2 / 2, 0, 1) in Python floats on the fp32 distance (faiss_index.py:86-88)."""
+    return [max(0.0, min(1.0, 1.0 - (float(d) / 2.0))) for d in D]
 
 
 class FAISSIndexReader:
@@ -136,6 +171,16 @@ async def search_faiss_by_vector(query_vector: List[float], limit: int = 50,
     if not index_files:
         logger.warning("No FAISS indices found")
         return []
+    if storage_mode() != "first":
+        corpus = get_corpus(str(storage_dir))
+        D, I = corpus.index.search(np.array([query_vector], dtype=np.float32), int(limit))
+        out = []
+        for row, score in zip(I[0], _reference_scores(D[0])):
+            h = corpus.hit_dict(int(row), score) if row >= 0 else None
+            if h is not None:
+                out.append(h)
+        logger.info("FAISS search returned %d results", len(out))
+        return out
     index_path = index_files[0]
     reader = FAISSIndexReader(index_path)
     hits = reader.search(query_vector, top_k=limit)
@@ -167,6 +212,14 @@ async def initialize_storage() -> None:
     if not os.path.isdir(str(storage_dir)):
         logger.warning("Storage directory not found: %s", storage_dir)
         return
+    if storage_mode() != "first":
+        try:
+            corpus = get_corpus(str(storage_dir))
+            logger.info("Initialized storage: %d documents (%d rows) concatenated into one index in HBM",
+                        len(corpus.docs), corpus.ntotal_global)
+        except Exception as e:
+            logger.error("Storage initialization failed: %s", e)
+        return
     count = 0
     for path in sorted(glob.glob(os.path.join(str(storage_dir), "*_faiss.index"))):
         try:
@@ -196,6 +249,18 @@ def build_bm25_sidecar(doc_id: str, chunk_texts: List[str], storage_dir: Optiona
     index = BM25Index.from_docs(docs, max(len(vocab), 1))
     bm_path, vocab_path = _sidecar_paths(storage_dir, doc_id)
     index.save(bm_path)
+    # the document's raw CSR: what the multi-document corpus is merged from (corpus-wide idf / avgdl need tf and
+    # doc_len, not the impacts folded with this document's own statistics)
+    from .bm25 import build_csr
+    from .corpus import csr_sidecar_path, save_doc_csr
+    doc_len = np.array([len(d) for d in docs], dtype=np.int32)
+    if doc_len.sum():
+        t = np.concatenate([np.asarray(d, dtype=np.int32) for d in docs if len(d)])
+        dd = np.repeat(np.arange(len(docs), dtype=np.int32), doc_len)
+    else:
+        t, dd = np.zeros(0, np.int32), np.zeros(0, np.int32)
+    indptr, pd, tf = build_csr(t, dd, len(docs), max(len(vocab), 1))
+    save_doc_csr(csr_sidecar_path(storage_dir, doc_id), indptr, pd, tf, doc_len, list(vocab.word_to_id.keys()))
     with open(vocab_path, "w", encoding="utf-8") as f:
         json.dump({"n_docs": len(docs), "words": list(vocab.word_to_id.keys())}, f, ensure_ascii=False)
     logger.info("Saved BM25 sidecar: %s (%d docs, %d terms)", bm_path, len(docs), len(vocab))
@@ -233,12 +298,27 @@ async def search_hybrid_by_vector(query_vector: List[float], query_text: str, li
     if not index_files:
         logger.warning("No FAISS indices found")
         return []
+    q = np.array([query_vector], dtype=np.float32)
+    limit = int(limit)
+    if storage_mode() != "first":
+        from .bm25 import cap_query_terms
+        corpus = get_corpus(storage_dir)
+        tokens = None
+        if corpus.bm25 is not None:
+            tokens = [cap_query_terms(corpus.vocab.encode(query_text or ""))]
+        scores, ids = HybridRetriever(corpus.index, corpus.bm25).retrieve(
+            q, tokens, top_k=limit, k_c=min(128, max(limit, config.CANDIDATE_DEPTH)))
+        out = []
+        for row, score in zip(ids[0], scores[0]):
+            h = corpus.hit_dict(int(row), float(score)) if row >= 0 else None
+            if h is not None:
+                out.append(h)
+        logger.info("Hybrid search returned %d results", len(out))
+        return out
     index_path = index_files[0]
     reader = FAISSIndexReader(index_path)
     doc_id = os.path.basename(index_path)[: -len(".index")].replace("_faiss", "")
     side = _load_bm25_sidecar(storage_dir, doc_id) if config.HYBRID_SEARCH_ENABLED else None
-    q = np.array([query_vector], dtype=np.float32)
-    limit = int(limit)
     if side is None:
         engine, tokens = HybridRetriever(reader.index, None), None
     else:

@@ -49,8 +49,14 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
     assert "LDTM" in sass, "no tcgen05.ld in SASS"
 
 
+def test_library_was_built_from_the_sources_in_the_tree():
+    """*.so is git-ignored: the hash of the sources compiled into the binary must match the tree, so a stale
+    library cannot pass for the committed code (build() rebuilds on a mismatch)."""
+    assert _lib.built_source_hash() == _lib.tree_source_hash()
+
+
 def test_version_and_launch_counter():
-    assert _lib.lib().hr_version() >= 100
+    assert _lib.lib().hr_version() >= 200
     assert _lib.launch_count() >= 0
 
 

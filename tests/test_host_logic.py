@@ -89,3 +89,65 @@ def test_retrieve_without_default_raises():
     retriever.set_default_retriever(None)
     with pytest.raises(RuntimeError, match="no retriever configured"):
         retriever.retrieve(np.zeros((1, 4), np.float32), [[1]], 3)
+
+
+def test_chunk_spans_follow_the_reference_row_mapping(tmp_path):
+    """row -> chunk = list({c["chunk_id"]: c ...}.values())[row] (/root/reference/rag/storage/faiss_index.py:175-181):
+    first position, last content of a repeated chunk_id; non-ASCII text (the reference saves with
+    ensure_ascii=False, file_storage.py:131-132) must not shift the byte offsets."""
+    from intool_rag_b200 import corpus
+    chunks = [{"chunk_id": f"c{i}", "page": i, "text": f"héllo wörld {i} ✓ \"quoted\" ]", "chunk_index": i} for i in range(6)]
+    chunks.append({"chunk_id": "c1", "page": 99, "text": "dup wins", "chunk_index": 1})
+    for kw in ({"indent": 2, "ensure_ascii": False}, {"ensure_ascii": True}, {"separators": (",", ":"), "ensure_ascii": False}):
+        p = tmp_path / "a_chunks.json"
+        p.write_text(json.dumps({"total": 6, "chunks": chunks}, **kw), encoding="utf-8")
+        want = list({c["chunk_id"]: c for c in chunks}.values())
+        store = corpus.ChunkStore([str(p)], [len(want) + 2])
+        assert [store.get(i) for i in range(len(want))] == want
+        assert store.get(len(want)) is None and store.get(-1) is None and store.get(10 ** 6) is None
+        assert store.table_bytes == (len(want) + 2) * 20
+        store.close()
+
+
+def test_merge_doc_csrs_equals_one_build_over_the_concatenation():
+    from intool_rag_b200 import corpus
+    rng = np.random.default_rng(0)
+    parts, row0, docs_all, r = [], [], [], 0
+    for f in range(4):
+        n = int(rng.integers(3, 9))
+        words = [f"w{j}" for j in rng.permutation(14)[:8]]
+        docs = [[int(x) for x in rng.integers(0, 8, size=int(rng.integers(1, 9)))] for _ in range(n)]
+        dl = np.array([len(x) for x in docs], np.int32)
+        t = np.concatenate([np.array(x, np.int32) for x in docs])
+        ip, pd, tf = pbm25.build_csr(t, np.repeat(np.arange(n, dtype=np.int32), dl), n, 8)
+        parts.append(dict(indptr=ip, post_doc=pd, post_tf=tf, doc_len=dl, words=words))
+        row0.append(r)
+        r += n
+        docs_all += [[words[x] for x in d] for d in docs]
+    for lo, hi in ((0, r), (4, r - 3), (r - 1, r), (2, 2)):
+        ip, pd, tf, dl, words, df_g, n_g, avg = corpus.merge_doc_csrs(parts, row0, lo, hi)
+        wid = {w: i for i, w in enumerate(words)}
+        t = np.concatenate([np.array([wid[w] for w in d], np.int32) for d in docs_all])
+        dlen = np.array([len(d) for d in docs_all])
+        dd = np.repeat(np.arange(r, dtype=np.int32), dlen)
+        full = pbm25.build_csr(t, dd, r, len(words))
+        m = (dd >= lo) & (dd < hi)
+        ip2, pd2, tf2 = pbm25.build_csr(t[m], dd[m] - lo, max(hi - lo, 1), len(words))
+        assert np.array_equal(ip, ip2) and np.array_equal(pd, pd2) and np.array_equal(tf, tf2)
+        assert np.array_equal(df_g, np.diff(full[0])) and n_g == r and avg == pytest.approx(dlen.mean(), rel=1e-15)
+        assert np.array_equal(dl, dlen[lo:hi])
+
+
+def test_flat_header_reader(tmp_path):
+    from intool_rag_b200 import corpus
+    from oracle import flat
+    ix = flat.IndexFlatL2(6)
+    ix.add(np.arange(30, dtype=np.float32).reshape(5, 6))
+    p = tmp_path / "d_faiss.index"
+    flat.write_index(ix, str(p))
+    assert corpus.read_flat_header(str(p)) == (6, 5, 1) and corpus.doc_id_of(str(p)) == "d"
+    rows = np.memmap(str(p), dtype="<f4", mode="r", offset=45, shape=(5, 6))
+    assert np.array_equal(np.asarray(rows), ix._x)
+    p.write_bytes(p.read_bytes()[:60])
+    with pytest.raises(RuntimeError, match="truncated"):
+        corpus.read_flat_header(str(p))
