@@ -102,10 +102,14 @@ fuse_kernel(const float* __restrict__ dD, const int64_t* __restrict__ dI, const 
 // (one list with kc = n_cand: the plain [nq][n_cand] layout; several lists: the all-gathered per-rank
 // buffers, read in place).
 constexpr int kMergeTopkCap = 2048;
+// sorted_lists != 0: every list is already best-first with its padding at the end (what hr_index_search /
+// hr_bm25_search produce): an entry's rank is its position in its own list plus, for every other list, the number
+// of entries that precede it there (one binary search each) — O(n L log kc) instead of the O(n^2) counting that an
+// arbitrary candidate set needs.  Equal (score, id) entries are ordered by list, then position.
 __global__ void __launch_bounds__(256)
 merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, int n_cand, int kc, int64_t s_stride,
                   int64_t i_stride, int k, int largest, float pad_score, float* __restrict__ oS,
-                  int64_t* __restrict__ oI) {
+                  int64_t* __restrict__ oI, int sorted_lists) {
   __shared__ float ss[kMergeTopkCap];
   __shared__ int64_t si[kMergeTopkCap];
   __shared__ int s_valid;
@@ -123,14 +127,33 @@ merge_topk_kernel(const float* __restrict__ S, const int64_t* __restrict__ I, in
   }
   __syncthreads();
   const int nv = s_valid;
+  const int n_lists = n_cand / kc;
   for (int e = threadIdx.x; e < n_cand; e += blockDim.x) {
     const int64_t id = si[e];
     if (id < 0) continue;
     const float f = ss[e];
     int rank = 0;
-    for (int j = 0; j < n_cand; ++j) {
-      const int64_t oj = si[j];
-      if (oj >= 0 && ranks_before_pos(ss[j], oj, j, f, id, e)) rank++;
+    if (sorted_lists) {
+      const int l = e / kc;
+      rank = e - l * kc;
+      for (int m = 0; m < n_lists; ++m) {
+        if (m == l) continue;
+        // first entry of list m that does NOT precede (f, id): padding never precedes
+        int lo = 0, hi = kc;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const int64_t oj = si[m * kc + mid];
+          const bool before = oj >= 0 && (ranks_before(ss[m * kc + mid], oj, f, id) ||
+                                          (m < l && ss[m * kc + mid] == f && oj == id));
+          if (before) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+    } else {
+      for (int j = 0; j < n_cand; ++j) {
+        const int64_t oj = si[j];
+        if (oj >= 0 && ranks_before_pos(ss[j], oj, j, f, id, e)) rank++;
+      }
     }
     if (rank < k) {
       oS[(size_t)q * k + rank] = largest ? f : -f;

@@ -1585,7 +1585,7 @@ extern "C" int hr_merge_topk(const float* S, const int64_t* I, int64_t nq, int n
   if (!S || !I || !out_S || !out_I) return set_err(HR_ERR_INVALID, "null argument");
   HR_DEVICE(device);
   merge_topk_kernel<<<(unsigned)nq, 256, 0, (cudaStream_t)stream>>>(S, I, n_cand, n_cand, 0, 0, k, largest, pad_score,
-                                                                    out_S, out_I);
+                                                                    out_S, out_I, 0);
   HR_LAUNCHED();
   return HR_OK;
 }
@@ -1653,10 +1653,10 @@ static int merge_fuse_enqueue(hr_index* ix, const float* D, const int64_t* I, co
     const int largest = ix->metric == HR_METRIC_INNER_PRODUCT;
     merge_topk_kernel<<<(unsigned)nq, 256, 0, st>>>(D, I, n_lists * kc, kc, list_stride_bytes / 4, list_stride_bytes / 8,
                                                     kc, largest, largest ? HR_NEG_INF : -HR_NEG_INF, rs.dD.as<float>(),
-                                                    rs.dI.as<int64_t>());
+                                                    rs.dI.as<int64_t>(), 1);
     HR_LAUNCHED();
     merge_topk_kernel<<<(unsigned)nq, 256, 0, st>>>(S, J, n_lists * kc, kc, list_stride_bytes / 4, list_stride_bytes / 8,
-                                                    kc, 1, 0.f, rs.bS.as<float>(), rs.bI.as<int64_t>());
+                                                    kc, 1, 0.f, rs.bS.as<float>(), rs.bI.as<int64_t>(), 1);
     HR_LAUNCHED();
     dD = rs.dD.as<float>();
     dI = rs.dI.as<int64_t>();
