@@ -463,16 +463,20 @@ def run_b200(args):
     d2h = args.nq * args.topk * 12
     step_e2e = lambda: engine.retrieve(q_host.numpy(), (qi_host.numpy(), qt_host.numpy()), args.topk)  # noqa: E731
 
+    dense_ms = [0.0]    # CUDA-event time of the dense part (pad .. fallback kernels) of a step, mean of the last timed() call
+
     def timed(fn, steps):
         """K steps bracketed by barrier + synchronize; CUDA events on the launch stream; max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         scan_ms, flagged, deeper = 0.0, 0, 0
+        dense_ms[0] = 0.0
         e0.record()
         for _ in range(steps):
             fn()
             st = ix.stats()
             scan_ms += st["scan_ms"]
+            dense_ms[0] += st["total_ms"] / steps
             flagged += st["flagged"]
             deeper += st["deeper"]
         e1.record()
@@ -492,6 +496,7 @@ def run_b200(args):
         sampler.start()
     l0 = _lib.launch_count()
     total_ms, scan_ms, flagged = timed(step_dev, args.steps)
+    dense_in_step_ms = dense_ms[0]
     launches = _lib.launch_count() - l0
     for _ in range(2):
         out_h = step_e2e()
@@ -586,6 +591,11 @@ def run_b200(args):
                 "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1_scan_bm25_ncu_full.md)",
                 "peak_source": pk["src"],
                 "kernel_ms": scan_ms, "share_of_step": scan_ms / ms_per_step,
+                "step_split_ms": {"dense_search_total": dense_in_step_ms, "scan_kernel": scan_ms,
+                                  "bm25_fusion_exchange_and_gaps": ms_per_step - dense_in_step_ms,
+                                  "note": "CUDA events of the library around the dense part of the timed steps; the rest of the step "
+                                          "is the BM25 search (timed alone below: roofline.bm25), fusion, at N > 1 the all-gather and "
+                                          "the merges, and what the power-capped clock costs the kernels that follow the scan"},
                 "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": corpus_bytes,
                 "hbm_gbs_algorithmic": corpus_bytes / scan_s / 1e9,
                 "hbm_frac_algorithmic": corpus_bytes / scan_s / 1e9 / pk["hbm_gbs"],

@@ -1412,11 +1412,13 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     const int64_t resident = (int64_t)h->num_sms * (wide ? 1 : 2) * kSwWarps;
     S = std::max<int64_t>((24 * resident + nq - 1) / nq, (h->N + 196607) / 196608);
     if (tuning().bm25_spans > 0) S = tuning().bm25_spans;
-    // Large batches keep one running top-k list per query under a lock (few jobs of a query run at the same
-    // time); in a small batch hundreds of jobs of one query finish together and would serialise there, so they
-    // write per-job slots that one merge kernel combines (S * k bounded by its sort buffer).
-    use_lock = nq >= 256;
-    S = std::max<int64_t>(1, std::min<int64_t>({S, nsl, use_lock ? (int64_t)1024 : (int64_t)(kBmMergeCap / k)}));
+    // Large batches keep one running top-k list per query under a lock: at most ~4 jobs of a query run at the
+    // same time.  In a smaller batch many jobs of one query finish together and would serialise there, so they
+    // write per-job slots that one merge kernel combines (S * k bounded by its sort buffer).  A job is at least 8
+    // slices long, or its epilogue (a 128-key sort) weighs as much as its work.
+    use_lock = nq * 4 >= resident;
+    S = std::max<int64_t>(1, std::min<int64_t>({S, std::max<int64_t>(1, nsl / 8),
+                                                use_lock ? (int64_t)1024 : (int64_t)(kBmMergeCap / k)}));
     if ((uint64_t)nq * (uint64_t)S >= 0xFFFF0000ull) return set_err(HR_ERR_INVALID, "bm25: too many (query, window) jobs");
   } else {
     // spans per query: ~8 waves of CTAs over the machine (kBsCtasPerSm resident per SM), bounded by the merge
