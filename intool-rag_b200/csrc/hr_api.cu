@@ -62,9 +62,7 @@ struct Tuning {
   int q_rows = 128;     // HR_QROWS: query rows materialised for the TMA box of small batches
   int pre_tiles = 4;    // HR_PRE_TILES: corpus tiles per CTA (pair) sampled by the threshold pre-pass
   int pre_rank = 2;     // HR_PRE_RANK: target corpus rank of the seeded threshold, in units of KL
-  int bm25_waves = 8;   // HR_BM25_WAVES: BM25 CTAs per resident slot
   bool no_pair = false; // HR_NO_PAIR: never use the cta_group::2 scan kernel
-  int bm25_impl = 0;    // HR_BM25_IMPL: 0 = flat-sweep kernel (bm25_sweep.cuh), 1 = round-1 slot kernel (bm25.cuh)
   int bm25_wide = 0;    // HR_BM25_WIDE: 1 = one CTA per SM with twice the slice (6144 docs) instead of two CTAs
   int bm25_spans = 0;   // HR_BM25_SPANS: doc windows per query (0 = automatic)
   int bm25_batch = 3;   // HR_BM25_BATCH: 3 = deeper load batch (3 iterations in flight; 4 on the wide variant), 2 = one less
@@ -81,9 +79,7 @@ static Tuning& tuning_mut() {
     x.q_rows = geti("HR_QROWS", x.q_rows, 1, 128);
     x.pre_tiles = geti("HR_PRE_TILES", x.pre_tiles, 1, 64);
     x.pre_rank = geti("HR_PRE_RANK", x.pre_rank, 1, 16);
-    x.bm25_waves = geti("HR_BM25_WAVES", x.bm25_waves, 1, 64);
     x.no_pair = getenv("HR_NO_PAIR") != nullptr;
-    x.bm25_impl = geti("HR_BM25_IMPL", 0, 0, 1);
     x.bm25_wide = geti("HR_BM25_WIDE", 0, 0, 1);
     x.bm25_spans = geti("HR_BM25_SPANS", 0, 0, 65535);
     x.bm25_batch = geti("HR_BM25_BATCH", 3, 2, 3);
@@ -228,9 +224,7 @@ extern "C" int hr_set_option(const char* name, int value) {
   if (n == "qrows") t.q_rows = clamp(value, 1, 128);
   else if (n == "pre_tiles") t.pre_tiles = clamp(value, 1, 64);
   else if (n == "pre_rank") t.pre_rank = clamp(value, 1, 16);
-  else if (n == "bm25_waves") t.bm25_waves = clamp(value, 1, 64);
   else if (n == "no_pair") t.no_pair = value != 0;
-  else if (n == "bm25_impl") t.bm25_impl = clamp(value, 0, 1);
   else if (n == "bm25_wide") t.bm25_wide = clamp(value, 0, 1);
   else if (n == "bm25_spans") t.bm25_spans = clamp(value, 0, 65535);
   else if (n == "bm25_batch") t.bm25_batch = clamp(value, 2, 3);
@@ -1392,10 +1386,8 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   }
   int kcp = 32;
   while (kcp < k) kcp <<= 1;
-  const bool sweep = tuning().bm25_impl == 0;
   const bool wide = tuning().bm25_wide != 0;
-  const int slice_docs = !sweep ? bs_slice_docs(kcp)
-                                : (kcp <= 64 ? (wide ? kSwSliceWideA : kSwSliceA) : (wide ? kSwSliceWideB : kSwSliceB));
+  const int slice_docs = kcp <= 64 ? (wide ? kSwSliceWideA : kSwSliceA) : (wide ? kSwSliceWideB : kSwSliceB);
   const int64_t nsl = std::max<int64_t>(1, (h->N + slice_docs - 1) / slice_docs);   // slices; nsl + 1 boundaries
   const int64_t nbc = (nsl + kBsCoarse - 1) / kBsCoarse + 1;                    // coarse boundaries
   const size_t nterm_slots = (size_t)std::max<int64_t>(n_terms, 1);
@@ -1405,7 +1397,7 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   int64_t S;   // doc windows (spans) per query
   int spc;     // slices per window
   bool use_lock = false;
-  if (sweep) {
+  {
     // jobs = (window, query), one warp each, drawn window-major by the resident warps.  Enough jobs for a
     // balanced tail (~24 per resident warp), windows small enough that the posting ranges all queries of the
     // batch read inside one window stay in L2 (~192k docs), bounded by the merge capacity.
@@ -1420,12 +1412,6 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     S = std::max<int64_t>(1, std::min<int64_t>({S, std::max<int64_t>(1, nsl / 8),
                                                 use_lock ? (int64_t)1024 : (int64_t)(kBmMergeCap / k)}));
     if ((uint64_t)nq * (uint64_t)S >= 0xFFFF0000ull) return set_err(HR_ERR_INVALID, "bm25: too many (query, window) jobs");
-  } else {
-    // spans per query: ~8 waves of CTAs over the machine (kBsCtasPerSm resident per SM), bounded by the merge
-    // capacity; a CTA wants at least one slice per warp
-    const int waves = tuning().bm25_waves;
-    S = ((int64_t)waves * kBsCtasPerSm * h->num_sms + nq - 1) / nq;
-    S = std::max<int64_t>(1, std::min<int64_t>({S, (nsl + kBsWarps - 1) / kBsWarps, (int64_t)(kBmMergeCap / k), (int64_t)65535}));
   }
   spc = (int)((nsl + S - 1) / S);
   S = (nsl + spc - 1) / spc;
@@ -1436,7 +1422,7 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   HR_TRY(h->plan_cur.ensure(cur_bytes));
   HR_TRY(h->plan_coarse.ensure(nterm_slots * (size_t)nbc * 4));
   HR_TRY(h->tau.ensure((size_t)nq * 8));
-  // sweep: running top-k list per query + count + lock; slot kernel: [nq][S][k] span lists
+  // large batches: running top-k list per query + count + lock; small ones: per-job slots [nq][S][k]
   HR_TRY(h->keys.ensure(use_lock ? (size_t)nq * k * 8 : (size_t)nq * S * k * 8));
   HR_TRY(h->ns.ensure(use_lock ? (size_t)nq * 8 : (size_t)nq * S * 4));
   HR_TRY(h->jobctr.ensure(4));
@@ -1464,7 +1450,7 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
                                                    h->plan_cur.as<uint32_t>());
     HR_LAUNCHED();
   }
-  if (sweep) {
+  {
     HR_CUDA(cudaMemsetAsync(h->jobctr.p, 0, 4, st));
     if (use_lock) HR_CUDA(cudaMemsetAsync(h->ns.p, 0, (size_t)nq * 8, st));   // gcount [nq] | glock [nq]
     const int smem = kSwWarps * sw_warp_bytes(slice_docs, kcp);
@@ -1504,25 +1490,6 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     HR_LAUNCHED();
     return HR_OK;
   }
-  {
-    const int smem = bs_smem_bytes(kcp);
-    dim3 grid((unsigned)nq, (unsigned)S);
-    auto launch = [&](auto kern) -> int {
-      HR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      kern<<<grid, kBsThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
-                                           h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
-                                           h->plan_cur.as<uint32_t>(), nsl, spc, (int)S, k, kcp, h->keys.as<uint64_t>(),
-                                           h->ns.as<int>(), h->tau.as<unsigned long long>());
-      HR_LAUNCHED();
-      return HR_OK;
-    };
-    if (slice_docs == kBsSliceLarge) HR_TRY(launch(bm25_slice_kernel<kBsSliceLarge>));
-    else HR_TRY(launch(bm25_slice_kernel<kBsSliceSmall>));
-  }
-  bm25_merge_kernel<<<(unsigned)nq, 256, 0, st>>>(h->keys.as<uint64_t>(), h->ns.as<int>(), (int)S, k, k, h->id_base,
-                                                  S_dev, I_dev);
-  HR_LAUNCHED();
-  return HR_OK;
 }
 
 static int bm25_check_plan(hr_bm25* h) {   // after a synchronisation of the stream bm25_search_dev ran on

@@ -3,8 +3,9 @@
 
     python tools/bm25_tune.py [rows] [vocab] [nq] [k] [variants]
 
-variants: comma list of impl:wide:spans (e.g. 1:0:0,0:0:0,0:1:0,0:0:32).  Every variant's (S, I) is compared bit
-for bit with the first one: all kernels sum a doc's terms in plan order, so the answers must be identical."""
+variants: comma list of wide:spans:batch (e.g. 0:0:3,1:0:3,0:32:3).  Every variant's (S, I) is compared bit for bit
+with the first one: every configuration sums a doc's terms in plan order, so the answers must be identical.  (Round 2
+used this tool to compare the flat-sweep kernel with the round-1 slot kernel, since removed: bit-identical at C1.)"""
 import os
 import sys
 import time
@@ -19,7 +20,7 @@ rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 vocab = int(sys.argv[2]) if len(sys.argv) > 2 else 30_000
 nq = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 k = int(sys.argv[4]) if len(sys.argv) > 4 else 50
-variants = sys.argv[5] if len(sys.argv) > 5 else "1:0:0,0:0:0,0:1:0"
+variants = sys.argv[5] if len(sys.argv) > 5 else "0:0:3,0:0:2,1:0:3"
 dev = torch.device("cuda", 0)
 t0 = time.time()
 indptr, post_doc, post_tf, doc_len = synth.sparse_corpus_csr_torch(rows, vocab, dev)
@@ -31,9 +32,8 @@ qi, qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
 print(f"setup {time.time() - t0:.1f}s nnz {bm.nnz}", flush=True)
 ref = None
 for v in variants.split(","):
-    impl, wide, spans, batch = (int(x) for x in (v.split(":") + ["3"])[:4])
+    wide, spans, batch = (int(x) for x in (v.split(":") + ["0", "3"])[:3])
     _lib.set_option("bm25_batch", batch)
-    _lib.set_option("bm25_impl", impl)
     _lib.set_option("bm25_wide", wide)
     _lib.set_option("bm25_spans", spans)
     for _ in range(3):
@@ -55,5 +55,5 @@ for v in variants.split(","):
         if not torch.equal(I, ref[1]):
             bad = (I != ref[1]).any(dim=1).nonzero().flatten()[:5].tolist()
             same += f" first differing queries {bad}"
-    print(f"variant impl={impl} wide={wide} spans={spans} batch={batch}: {m:.3f} ms (min {min(ms):.3f}) postings {touched} "
+    print(f"variant wide={wide} spans={spans} batch={batch}: {m:.3f} ms (min {min(ms):.3f}) postings {touched} "
           f"{touched * 8 / m / 1e6:.1f} GB/s algorithmic{same}", flush=True)
