@@ -604,6 +604,9 @@ def run_b200(args):
                 "bm25": {"kernel": "bm25_sweep_kernel (+ plan and merge kernels)", "bound": "hbm", "postings": int(touched), "ms": bm_ms,
                          "achieved": touched * 8 / (bm_ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": touched * 8 / (bm_ms / 1e3) / 1e9 / pk["hbm_gbs"],
+                         # dram bytes of the sweep kernel + the two cursor-plan kernels, ncu capture of this default
+                         # workload (profiles/r2_bm25_sweep_ncu.md); other workloads: not captured
+                         "traffic": (5.859e9 + 0.022e9 + 0.645e9 + 2.418e9 + 0.208e9) if traffic is not None else None,
                          "algorithmic_bytes": "8 B per posting of every (query, term) pair; lists shared by the queries of a "
                                               "batch are read from HBM once per doc window and from L2 afterwards "
                                               "(profiles/r2_bm25_sweep_ncu.md)"}}
