@@ -8,7 +8,7 @@ k1=1.5, b=0.75, Lucene idf by default, duplicate query terms count per occurrenc
 from __future__ import annotations
 
 import ctypes as C
-from typing import Iterable, List, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 

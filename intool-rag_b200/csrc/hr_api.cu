@@ -1740,7 +1740,7 @@ extern "C" int hr_comm_init(const void* unique_id_128_bytes, int rank, int world
   if (!out) return set_err(HR_ERR_INVALID, "null out");
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) return set_err(HR_ERR_INVALID, "bad rank / world");
-  if ((int64_t)world * 1 > kMergeTopkCap) return set_err(HR_ERR_INVALID, "world too large");
+  if (world > kMergeTopkCap) return set_err(HR_ERR_INVALID, "world too large (the merge handles world * kc <= 2048 candidates per query)");
   int ndev = 0;
   HR_TRY(hr_device_count(&ndev));
   if (ndev <= 0) return set_err(HR_ERR_CUDA, "no CUDA device (hr_b200 has no CPU fallback)");

@@ -15,12 +15,9 @@ Differences, all additive:
 """
 from __future__ import annotations
 
-import asyncio
 import inspect
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional
-
-import numpy as np
 
 from . import _lib, storage
 
