@@ -958,6 +958,9 @@ struct hr_bm25 {
   DevBuf keys, ns, io_qi, io_qt, io_S, io_I, touched, plan_nt, plan_start, plan_len, plan_wgt, plan_cur, plan_coarse, tau,
       jobctr, plan_err;
   int* h_plan_err = nullptr;   // pinned copy of plan_err (queries with too many distinct terms in the last search)
+  // batch-1 / batch-2 searches run next to the dense scan on this stream (candidates_enqueue)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::mutex mu;               // one search at a time per handle (the scratch above is per handle)
 };
 
@@ -970,6 +973,9 @@ extern "C" int hr_bm25_destroy(hr_bm25* h) {
   if (h->post_imp) cudaFree(h->post_imp);
   if (h->idf) cudaFree(h->idf);
   if (h->h_plan_err) cudaFreeHost(h->h_plan_err);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   DevBuf* bufs[] = {&h->keys,    &h->ns,         &h->io_qi,    &h->io_qt,    &h->io_S,     &h->io_I, &h->touched,
                     &h->plan_nt, &h->plan_start, &h->plan_len, &h->plan_wgt, &h->plan_cur, &h->plan_coarse, &h->tau,
                     &h->jobctr,  &h->plan_err};
@@ -1373,8 +1379,11 @@ extern "C" int hr_bm25_load(const char* path, int device, hr_bm25** out) {
 }
 
 // device-pointer search; does not synchronise.  n_terms = length of q_terms (sizes the plan).
+// narrow: one-warp CTAs (14 KB of shared memory each) that fit on an SM NEXT TO a persistent dense-scan CTA: the
+// batch-1 search then runs concurrently with the scan instead of in front of it.
 static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_dev, int64_t nq, int64_t n_terms,
-                           int k, float* S_dev, int64_t* I_dev, cudaStream_t st, unsigned long long* touched_dev) {
+                           int k, float* S_dev, int64_t* I_dev, cudaStream_t st, unsigned long long* touched_dev,
+                           bool narrow = false) {
   if (nq == 0) return HR_OK;
   if (k > kBmMaxK) return set_err(HR_ERR_INVALID, "bm25: k must be <= 128");
   if (nq >= (int64_t)0x7FFFFFF0ll) return set_err(HR_ERR_INVALID, "bm25: too many queries in one call");
@@ -1401,7 +1410,7 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
     // jobs = (window, query), one warp each, drawn window-major by the resident warps.  Enough jobs for a
     // balanced tail (~24 per resident warp), windows small enough that the posting ranges all queries of the
     // batch read inside one window stay in L2 (~192k docs), bounded by the merge capacity.
-    const int64_t resident = (int64_t)h->num_sms * (wide ? 1 : 2) * kSwWarps;
+    const int64_t resident = narrow ? (int64_t)h->num_sms : (int64_t)h->num_sms * (wide ? 1 : 2) * kSwWarps;
     S = std::max<int64_t>((24 * resident + nq - 1) / nq, (h->N + 196607) / 196608);
     if (tuning().bm25_spans > 0) S = tuning().bm25_spans;
     // Large batches keep one running top-k list per query under a lock: at most ~4 jobs of a query run at the
@@ -1453,12 +1462,13 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   {
     HR_CUDA(cudaMemsetAsync(h->jobctr.p, 0, 4, st));
     if (use_lock) HR_CUDA(cudaMemsetAsync(h->ns.p, 0, (size_t)nq * 8, st));   // gcount [nq] | glock [nq]
-    const int smem = kSwWarps * sw_warp_bytes(slice_docs, kcp);
+    const int warps = narrow ? 1 : kSwWarps;
+    const int smem = warps * sw_warp_bytes(slice_docs, kcp);
     const int64_t njobs = nq * S;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->num_sms * (wide ? 1 : 2), (njobs + kSwWarps - 1) / kSwWarps));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->num_sms * (narrow || wide ? 1 : 2), (njobs + warps - 1) / warps));
     auto launch = [&](auto kern) -> int {
-      HR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      kern<<<grid, kSwThreads, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
+      HR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwWarps * sw_warp_bytes(slice_docs, kcp)));
+      kern<<<grid, 32 * warps, smem, st>>>(h->post_doc, h->post_imp, qi_dev, h->plan_nt.as<int>(),
                                            h->plan_start.as<int64_t>(), h->plan_wgt.as<float>(),
                                            h->plan_cur.as<uint32_t>(), nsl, spc, (int)S, (int)nq, k, kcp,
                                            h->keys.as<uint64_t>(), h->ns.as<int>(), h->ns.as<int>() + nq,
@@ -1597,6 +1607,26 @@ extern "C" int hr_rank_pages(const float* S, const int64_t* I, int64_t nq, int k
 static int candidates_enqueue(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* qi, const int32_t* qt,
                               int64_t nq, int64_t n_terms, int kc, float* D, int64_t* I, float* S, int64_t* J,
                               cudaStream_t st) {
+  if (bm && nq <= 2 && ix->ntotal > 0) {
+    // Latency mode (the reference's real operating point: one query, rag/storage/faiss_index.py:81): BM25 on a
+    // side stream in one-warp CTAs that share the SMs with the persistent scan CTAs; the step then takes what the
+    // dense search takes.  (For batches the two are serialised: the scan is power-bound and nothing overlaps.)
+    if (!bm->side) {
+      if (cudaStreamCreateWithFlags(&bm->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&bm->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&bm->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return set_err(HR_ERR_CUDA, "could not create the BM25 side stream");
+      }
+    }
+    HR_CUDA(cudaEventRecord(bm->ev_fork, st));
+    HR_CUDA(cudaStreamWaitEvent(bm->side, bm->ev_fork, 0));
+    HR_TRY(bm25_search_dev(bm, qi, qt, nq, n_terms, kc, S, J, bm->side, nullptr, true));
+    HR_CUDA(cudaEventRecord(bm->ev_join, bm->side));
+    HR_TRY(index_search_enqueue(ix, q, nq, kc, D, I, st));
+    HR_CUDA(cudaStreamWaitEvent(st, bm->ev_join, 0));
+    return HR_OK;
+  }
   if (bm) {
     HR_TRY(bm25_search_dev(bm, qi, qt, nq, n_terms, kc, S, J, st, nullptr));
   } else {
