@@ -1607,10 +1607,12 @@ extern "C" int hr_rank_pages(const float* S, const int64_t* I, int64_t nq, int k
 static int candidates_enqueue(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* qi, const int32_t* qt,
                               int64_t nq, int64_t n_terms, int kc, float* D, int64_t* I, float* S, int64_t* J,
                               cudaStream_t st) {
-  if (bm && nq <= 2 && ix->ntotal > 0) {
+  if (bm && nq <= 16 && ix->ntotal > 0) {
     // Latency mode (the reference's real operating point: one query, rag/storage/faiss_index.py:81): BM25 on a
-    // side stream in one-warp CTAs that share the SMs with the persistent scan CTAs; the step then takes what the
-    // dense search takes.  (For batches the two are serialised: the scan is power-bound and nothing overlaps.)
+    // side stream in one-warp CTAs that share the SMs with the persistent scan CTAs (16 KB of shared memory are
+    // free next to one); the step then takes what the dense search takes.  One warp per SM scores ~10 queries in
+    // the time the HBM-bound scan needs, hence the limit; bigger batches are serialised (their scan is
+    // tensor- and power-bound and nothing overlaps: DESIGN.md section 4).
     if (!bm->side) {
       if (cudaStreamCreateWithFlags(&bm->side, cudaStreamNonBlocking) != cudaSuccess ||
           cudaEventCreateWithFlags(&bm->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
