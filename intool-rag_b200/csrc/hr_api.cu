@@ -172,6 +172,10 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int ld_elem
 // -------------------------------------------------------------------------------------------------
 struct RetrieveScratch {
   DevBuf q, qi, qt, dD, dI, bS, bI, oS, oI;
+  // host-io calls upload the query embeddings on this stream while the BM25 kernels (which only need the token
+  // ids) already run on the caller's stream
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_copied = nullptr, ev_free = nullptr;
 };
 
 struct hr_index {
@@ -308,6 +312,9 @@ extern "C" int hr_index_destroy(hr_index* h) {
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->rs.copy) cudaStreamDestroy(h->rs.copy);
+  if (h->rs.ev_copied) cudaEventDestroy(h->rs.ev_copied);
+  if (h->rs.ev_free) cudaEventDestroy(h->rs.ev_free);
   delete h;
   return HR_OK;
 }
@@ -1606,7 +1613,7 @@ extern "C" int hr_rank_pages(const float* S, const int64_t* I, int64_t nq, int k
 // BM25 then dense for one shard, all enqueued on `st` (no synchronisation): S,J then D,I [nq,kc] on the device
 static int candidates_enqueue(hr_index* ix, hr_bm25* bm, const float* q, const int32_t* qi, const int32_t* qt,
                               int64_t nq, int64_t n_terms, int kc, float* D, int64_t* I, float* S, int64_t* J,
-                              cudaStream_t st) {
+                              cudaStream_t st, cudaEvent_t q_ready = nullptr) {
   if (bm && nq <= 16 && ix->ntotal > 0) {
     // Latency mode (the reference's real operating point: one query, rag/storage/faiss_index.py:81): BM25 on a
     // side stream in one-warp CTAs that share the SMs with the persistent scan CTAs (16 KB of shared memory are
@@ -1635,6 +1642,7 @@ static int candidates_enqueue(hr_index* ix, hr_bm25* bm, const float* q, const i
     fill_pad_kernel<<<(int)std::min<int64_t>((nq * kc + 255) / 256, 1024), 256, 0, st>>>(S, J, nq * kc, 0.f);
     HR_LAUNCHED();
   }
+  if (q_ready) HR_CUDA(cudaStreamWaitEvent(st, q_ready, 0));   // embeddings uploaded on another stream meanwhile
   return index_search_enqueue(ix, q, nq, kc, D, I, st);
 }
 
@@ -1870,9 +1878,28 @@ static int retrieve_impl(hr_comm* c, hr_index* ix, hr_bm25* bm, const float* q, 
   const int32_t* qtd = q_terms;
   float* oS = out_S;
   int64_t* oI = out_I;
+  bool q_on_copy_stream = false;
   if (!io_on_device) {
     HR_TRY(rs.q.ensure((size_t)nq * ix->d * 4));
-    HR_CUDA(cudaMemcpyAsync(rs.q.p, q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
+    if (bm && nq > 16) {
+      // a batch: BM25 runs first and only needs the token ids, so the embeddings (nq * d * 4 bytes) travel on a
+      // second stream meanwhile; the dense search waits for them (candidates_enqueue)
+      if (!rs.copy) {
+        if (cudaStreamCreateWithFlags(&rs.copy, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&rs.ev_copied, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&rs.ev_free, cudaEventDisableTiming) != cudaSuccess) {
+          (void)cudaGetLastError();
+          return set_err(HR_ERR_CUDA, "could not create the upload stream");
+        }
+      }
+      HR_CUDA(cudaEventRecord(rs.ev_free, st));              // whatever used rs.q before on `st` is ordered first
+      HR_CUDA(cudaStreamWaitEvent(rs.copy, rs.ev_free, 0));
+      HR_CUDA(cudaMemcpyAsync(rs.q.p, q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, rs.copy));
+      HR_CUDA(cudaEventRecord(rs.ev_copied, rs.copy));
+      q_on_copy_stream = true;
+    } else {
+      HR_CUDA(cudaMemcpyAsync(rs.q.p, q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
+    }
     qd = rs.q.as<float>();
     if (bm) {
       HR_TRY(check_query_csr_host(q_indptr, nq));
@@ -1891,7 +1918,8 @@ static int retrieve_impl(hr_comm* c, hr_index* ix, hr_bm25* bm, const float* q, 
     oI = rs.oI.as<int64_t>();
   }
   // BM25, dense (decisions on the device), exchange, merge + fusion: one stream, no host round-trip in between
-  HR_TRY(candidates_enqueue(ix, bm, qd, qid, qtd, nq, n_terms, kc, lD, lI, lS, lJ, st));
+  HR_TRY(candidates_enqueue(ix, bm, qd, qid, qtd, nq, n_terms, kc, lD, lI, lS, lJ, st,
+                            q_on_copy_stream ? rs.ev_copied : nullptr));
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (world > 1) {
       NcclApi* a = nccl_api();
