@@ -54,7 +54,7 @@ while time.time() < t_end:
     nd = int(rng.choice([1, 50, 3000, 20000, 70000]))
     V = int(rng.choice([5, 200, 3000]))
     t, dd, dl = synth.sparse_corpus_np(nd, V, seed=int(rng.integers(1 << 30)), mean_len=float(rng.choice([8.0, 40.0])))
-    nqs = int(rng.choice([1, 3, 40]))
+    nqs = int(rng.choice([1, 3, 40, 700]))    # 700: the running-list (lock) mode of the sweep kernel
     qs = synth.sparse_queries_np(nqs, V, seed=int(rng.integers(1 << 30)), stop=min(4, V - 1))
     if nqs > 2:
         qs[0] = []
