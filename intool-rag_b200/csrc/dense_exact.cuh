@@ -360,8 +360,10 @@ exact_merge_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
 // tprime [nq] = upper bound on the APPROXIMATE score of every row that is not in the shortlist
 // (HR_NEG_INF when nothing was dropped).  A query is certified when its exact k-th best, mapped to
 // the filter's score domain, beats tprime by more than the filter's worst-case error eps.
+// Block size: 256 threads, or 1024 for small batches (a warp re-scores one row at a time: with few blocks in
+// flight the rows of a query are a latency chain, and 32 warps make it 4x shorter).
 template <typename T, int METRIC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict__ qpad,
                         const uint32_t* __restrict__ short_rows, int row_stride, const int* __restrict__ short_n,
                         const float* __restrict__ tprime, int KL, int k, float c_acc, int filter_kind,

@@ -611,13 +611,14 @@ static int launch_rescore(hr_index* h, int nb, int KL, int k, float c_acc, float
   const int* qsel = stage2 ? h->deeper.as<int>() : nullptr;
   int* deeper = stage2 ? nullptr : h->deeper.as<int>();
   const int* nsel_dev = stage2 ? h->counters.as<int>() + 2 : nullptr;
+  const int threads = nb <= 32 ? 1024 : 256;
   if (h->metric == HR_METRIC_INNER_PRODUCT)
-    rescore_finalize_kernel<T, kMetricIP><<<nb, 256, smem, st>>>(
+    rescore_finalize_kernel<T, kMetricIP><<<nb, threads, smem, st>>>(
         (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), kShortCap, n_in, tp, depth, k, c_acc,
         fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(), h->counters.as<int>(), qsel,
         h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2, h->short_s.as<float>(), nsel_dev);
   else
-    rescore_finalize_kernel<T, kMetricL2><<<nb, 256, smem, st>>>(
+    rescore_finalize_kernel<T, kMetricL2><<<nb, threads, smem, st>>>(
         (const T*)h->x, h->ld, h->qpad.as<float>(), h->short_rows.as<uint32_t>(), kShortCap, n_in, tp, depth, k, c_acc,
         fk, h->max_norm2, h->id_base, D, I, h->flagged.as<int>(), h->counters.as<int>(), qsel,
         h->short_tot.as<int>(), deeper, h->counters.as<int>() + 2, h->short_s.as<float>(), nsel_dev);
