@@ -60,7 +60,9 @@ static int set_err(int code, const std::string& msg) {
 // Tuning knobs, read once from the environment (defaults are the measured best on B200).
 struct Tuning {
   int q_rows = 128;     // HR_QROWS: query rows materialised for the TMA box of small batches
-  int pre_tiles = 4;    // HR_PRE_TILES: corpus tiles per CTA (pair) sampled by the threshold pre-pass
+  int pre_tiles = 4;    // HR_PRE_TILES: corpus tiles per CTA pair sampled by the threshold pre-pass (batches > 128)
+  int pre_tiles_small = 1;  // HR_PRE_TILES_SMALL: the same for batches of up to 128 queries (HBM-bound scan: a
+                            // sparser sample costs less than the few extra list insertions it causes)
   int pre_rank = 2;     // HR_PRE_RANK: target corpus rank of the seeded threshold, in units of KL
   bool no_pair = false; // HR_NO_PAIR: never use the cta_group::2 scan kernel
   int bm25_wide = 0;    // HR_BM25_WIDE: 1 = one CTA per SM with twice the slice (6144 docs) instead of two CTAs
@@ -78,6 +80,7 @@ static Tuning& tuning_mut() {
     };
     x.q_rows = geti("HR_QROWS", x.q_rows, 1, 128);
     x.pre_tiles = geti("HR_PRE_TILES", x.pre_tiles, 1, 64);
+    x.pre_tiles_small = geti("HR_PRE_TILES_SMALL", x.pre_tiles_small, 1, 64);
     x.pre_rank = geti("HR_PRE_RANK", x.pre_rank, 1, 16);
     x.no_pair = getenv("HR_NO_PAIR") != nullptr;
     x.bm25_wide = geti("HR_BM25_WIDE", 0, 0, 1);
@@ -227,6 +230,7 @@ extern "C" int hr_set_option(const char* name, int value) {
   auto clamp = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
   if (n == "qrows") t.q_rows = clamp(value, 1, 128);
   else if (n == "pre_tiles") t.pre_tiles = clamp(value, 1, 64);
+  else if (n == "pre_tiles_small") t.pre_tiles_small = clamp(value, 1, 64);
   else if (n == "pre_rank") t.pre_rank = clamp(value, 1, 16);
   else if (n == "no_pair") t.no_pair = value != 0;
   else if (n == "bm25_wide") t.bm25_wide = clamp(value, 0, 1);
@@ -732,7 +736,8 @@ static int chunk_enqueue(hr_index* h, const float* q_dev, int nb, int k, float* 
   // from fewer maxima (j = 8) landed inside the top 100 rows of a 5M-row shard for about 1 query in 10^4 and sent
   // it to the exact scan: 16 ms for one query.
   const int units = use_pair ? std::max(1, h->num_sms / 2) : h->num_sms;
-  int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (tuning().pre_tiles * units)));
+  const int pre_tiles = use_pair ? tuning().pre_tiles : tuning().pre_tiles_small;
+  int stride = std::max(1, std::min(kSampleStrideMax, num_ctiles / (pre_tiles * units)));
   stride = std::min(stride, 32);
   stride = std::max(stride, (num_ctiles + kSeedCap - 1) / kSeedCap);
   if (stride > 1) {
