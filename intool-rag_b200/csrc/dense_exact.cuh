@@ -421,8 +421,6 @@ rescore_finalize_kernel(const T* __restrict__ x, int ld, const float* __restrict
       if (ss[i] < cut && ss[i - 1] >= cut) s_need = i;   // sorted descending: exactly one boundary (or none)
     __syncthreads();
   }
-  const int n_all = n;
-  (void)n_all;
   const int nn = s_need;
   for (int i = warp; i < nn; i += nwarp) {
     uint32_t row = short_rows[(int64_t)q * row_stride + i];
