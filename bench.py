@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--nq", type=int, default=int(os.getenv("HR_BENCH_NQ", 1024)))
     ap.add_argument("--vocab", type=int, default=30_000)
     ap.add_argument("--topk", type=int, default=10)
-    ap.add_argument("--cpu-sample-rows", type=int, default=int(os.getenv("HR_BENCH_CPU_ROWS", 200_000)))
+    ap.add_argument("--cpu-sample-rows", type=int, default=int(os.getenv("HR_BENCH_CPU_ROWS", 500_000)))
     ap.add_argument("--storage", default=os.getenv("HR_BENCH_STORAGE", "f32+bf16"), choices=["f32", "f32+bf16", "bf16"],
                     help="f32: fp32 rows, TF32 filter; f32+bf16: fp32 rows + bf16 shadow for the filter (same answers, "
                          "1.5x the memory); bf16: bf16 rows")
@@ -159,7 +159,7 @@ def run_reference(args):
     rank = int(os.getenv("RANK", "0"))
     if rank != 0:
         return
-    # the requested K / W are honoured (a step of the 200k-row sample takes ~2 s on 16 cores); only absurd values are
+    # the requested K / W are honoured (a step of the 500k-row sample takes ~5 s on 16 cores); only absurd values are
     # clamped so that the arm always ends within a few minutes
     steps, warmup = max(1, min(args.steps, 20)), max(0, min(args.warmup, 5))
     cb = cpu_reference(args, steps, warmup)
@@ -746,7 +746,7 @@ def run_b200(args):
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference(args, steps=1, warmup=1)
+            line["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1)   # ~15 s of CPU work on 16 cores
         print(json.dumps(line), file=_json_out, flush=True)
     if world > 1:
         dist.barrier()
