@@ -250,7 +250,7 @@ exact_scan_kernel(const T* __restrict__ x, int64_t N, int ld, const float* __res
           float s = (METRIC == kMetricIP) ? sc[f] : -sc[f];
           uint64_t key = make_key(s, (uint32_t)r);
           uint64_t thr = (cnt[f] == k) ? (minkey[f] > tg[f] ? minkey[f] : tg[f]) : tg[f];
-          if (key > thr) {
+          if (s == s && key > thr) {   // a NaN score is never a candidate (faiss' heap test is false for NaN)
             volatile uint64_t* lst = lists + ((int64_t)(g0 + f) * W + gw) * k;
             warp_list_insert(lst, k, cnt[f], minkey[f], key, lane);
             if (cnt[f] == k && minkey[f] > tg[f]) {

@@ -194,7 +194,7 @@ struct hr_index {
   DevBuf qpad, qh, lists, cnts, tau_g, short_rows, short_s, short_n, short_tot, tprime, tprime_tot, flagged, deeper,
       counters, pre_max;
   DevBuf ex_lists, ex_cnts, ex_tau, ex_sel, io_q, io_D, io_I, stage;
-  int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow [2]=ndeeper
+  int* h_counters = nullptr;  // pinned: [0]=nflag [1]=overflow [2]=ndeeper [3]=max |x|^2 (ordered uint)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   hr_scan_stats stats{};
   // a chunk whose device-side counters have not been read back yet (chunk_enqueue / chunk_finish)
@@ -780,6 +780,7 @@ static int chunk_enqueue(hr_index* h, const float* q_dev, int nb, int k, float* 
     HR_TRY(launch_exact<__nv_bfloat16>(h, h->flagged.as<int>(), cap, k, Db, Ib, st, h->counters.as<int>()));
   }
   HR_CUDA(cudaMemcpyAsync(h->h_counters, h->counters.p, 12, cudaMemcpyDeviceToHost, st));
+  HR_CUDA(cudaMemcpyAsync(h->h_counters + 3, h->max_norm2, 4, cudaMemcpyDeviceToHost, st));
   h->pend = true;
   h->pend_cap = cap;
   h->pend_k = k;
@@ -797,6 +798,14 @@ static int chunk_finish(hr_index* h, cudaStream_t st, bool* changed) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.scan_ms += ms;
   const int nflag = h->h_counters[0];
+  if (nflag > 0 && !std::isfinite(ord2f((uint32_t)h->h_counters[3]))) {
+    // a row with a NaN / Inf component (or |x| > 1.8e19): the filter's error bound is unbounded, no query can be
+    // certified, every search takes the exhaustive exact scan (same answers; such rows are never returned)
+    static std::atomic<bool> warned{false};
+    if (!warned.exchange(true))
+      fprintf(stderr, "hr_b200: the index holds rows whose squared norm is not finite; every query runs the exhaustive "
+                      "exact scan (remove NaN / Inf rows to get the tensor-core path back)\n");
+  }
   h->stats.flagged += nflag;
   h->stats.overflow += h->h_counters[1];
   h->stats.deeper += h->h_counters[2];

@@ -50,9 +50,20 @@ def topk_rows(scores: np.ndarray, k: int, largest: bool) -> Tuple[np.ndarray, np
     if n == 0 or k == 0:
         return out_v, out_i
     key = -scores if largest else scores  # ascending key == best first
-    kk = min(k, n)
     for r in range(nq):
         row = key[r]
+        kk = min(k, n)
+        nan = np.isnan(row)
+        if nan.any():
+            # a NaN score is never a candidate: faiss' heap test `C::cmp(heap_top, score)` is false for NaN, so a
+            # query (or corpus row) with a NaN component yields padding (by recollection)
+            cand = np.nonzero(~nan)[0]
+            kk = min(k, cand.size)
+            order = np.lexsort((cand, row[cand]))[:kk]
+            sel = cand[order]
+            out_i[r, :kk] = sel
+            out_v[r, :kk] = scores[r, sel]
+            continue
         if n > 4 * kk:
             # candidates: everything <= kth key (keeps all boundary ties), then exact sort
             kth = np.partition(row, kk - 1)[kk - 1]

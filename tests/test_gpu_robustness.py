@@ -224,3 +224,39 @@ def test_k_above_128_runs_the_exact_scan(gpu):
     Dr, Ir = o.search(q, 300)
     assert (I == Ir).mean() > 0.999
     np.testing.assert_allclose(D, Dr, atol=3e-6)
+
+
+@pytest.mark.parametrize("storage", ["f32", "f32+bf16", "bf16"])
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_non_finite_inputs_follow_the_nan_rule(gpu, storage, metric):
+    """NaN scores are never candidates (oracle/flat.py: faiss' heap test is false for NaN): a NaN query gets padding,
+    a NaN corpus row is never returned, in the tensor-core path and in the exhaustive one alike; nothing hangs."""
+    rng = np.random.default_rng(9)
+    n, d = 30000, 96
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    if storage == "bf16":
+        import torch
+        x = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    q = rng.standard_normal((6, d)).astype(np.float32)
+    o = (flat.IndexFlatIP if metric == "ip" else flat.IndexFlatL2)(d)
+    o.add(x)
+    _, I0 = o.search(q, 10)
+    victim = int(I0[0, 0])
+    x[victim, 7] = np.nan
+    q[1, 2] = np.nan
+    q[2, :] = 0.0
+    o = (flat.IndexFlatIP if metric == "ip" else flat.IndexFlatL2)(d)
+    o.add(x)
+    Do, Io = o.search(q, 10, precision="f64")
+    ix = (hf.IndexFlatIP if metric == "ip" else hf.IndexFlatL2)(d, storage=storage)
+    ix.add(x)
+    for mode in ("auto", "exact"):
+        ix.set_mode(mode)
+        D, I = ix.search(q, 10)
+        assert (I[1] == -1).all(), mode
+        assert victim not in I
+        for r in (0, 3, 4, 5):      # generic rows: ids equal the fp64 oracle (gaps are far above fp32 rounding)
+            assert np.array_equal(I[r], Io[r]), (mode, r)
+        if metric == "ip":           # the zero query ties every finite row at 0: smallest ids first, NaN row skipped
+            want = [i for i in range(12) if i != victim][:10]
+            assert list(I[2]) == want, mode

@@ -226,3 +226,26 @@ def test_page_ranking_golden_from_the_reference_run(golden_dir):
         assert [r[0] for r in got] == [r[0] for r in ranking], qname
         assert [r[2] for r in got] == [r[2] for r in ranking], qname
         np.testing.assert_allclose([r[1] for r in got], [r[1] for r in ranking], rtol=1e-12)
+
+
+def test_nan_scores_are_never_candidates():
+    """faiss' heap test is false for NaN (by recollection): a query with a NaN component
+    gets padding, a corpus row with a NaN component is never returned; the other answers are untouched."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((300, 16)).astype(np.float32)
+    q = rng.standard_normal((3, 16)).astype(np.float32)
+    for make in (flat.IndexFlatIP, flat.IndexFlatL2):
+        clean = make(16)
+        clean.add(x)
+        D0, I0 = clean.search(q, 5)
+        xb = x.copy()
+        victim = int(I0[0, 0])
+        xb[victim, 3] = np.nan
+        qb = q.copy()
+        qb[1, 0] = np.nan
+        ix = make(16)
+        ix.add(xb)
+        D, I = ix.search(qb, 5)
+        assert (I[1] == -1).all() and np.all(np.abs(D[1]) == flat.FLT_MAX)
+        assert victim not in I[0] and victim not in I[2]
+        assert list(I[0][:4]) == [i for i in I0[0] if i != victim][:4]
