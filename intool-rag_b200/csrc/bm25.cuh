@@ -184,25 +184,30 @@ bm25_plan_terms_kernel(const int64_t* __restrict__ indptr, const int64_t* __rest
 
 // ---- plan, step 2: cursor table --------------------------------------------------------------------
 // cur[(size_t)q_indptr[q] * nb + j * nt + u] = number of postings of term u with doc < j * bdocs, for the nb
-// boundaries j = 0..nb-1 (the last one is the end of the list).  Thread = boundary j (consecutive threads
-// search consecutive boundaries of the same list, so the searches share cache lines), looping over the
-// query's terms.  With `coarse` != nullptr the search runs inside [coarse[j / ratio], coarse[j / ratio + 1]]
-// (a table of the same layout with nbc boundaries every ratio * bdocs docs).
+// boundaries j = 0..nb-1 (the last one is the end of the list).  Thread = (term group g, boundary j): consecutive
+// threads search consecutive boundaries of the same list, so the searches share cache lines; a thread handles the
+// terms g, g + G, ... of the query.  G = 1 for big tables (enough threads anyway); small tables (a shard, the coarse
+// level) use up to 8 groups, or the chain of nt dependent binary searches per thread is all the kernel's time.
+// With `coarse` != nullptr the search runs inside [coarse[j / ratio], coarse[j / ratio + 1]] (a table of the same
+// layout with nbc boundaries every ratio * bdocs docs).
 __global__ void __launch_bounds__(256)
 bm25_plan_cursors_kernel(const int32_t* __restrict__ post_doc, const int32_t* __restrict__ q_indptr,
                          const int* __restrict__ plan_nt, const int64_t* __restrict__ plan_start,
                          const uint32_t* __restrict__ plan_len, int64_t nb, int64_t bdocs,
-                         const uint32_t* __restrict__ coarse, int64_t nbc, int ratio, uint32_t* __restrict__ cur) {
+                         const uint32_t* __restrict__ coarse, int64_t nbc, int ratio, uint32_t* __restrict__ cur,
+                         int G) {
   const int q = blockIdx.x;
   const int nt = plan_nt[q];
-  const int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-  if (j >= nb || nt == 0) return;
+  const int64_t idx = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  const int g = (int)(idx / nb);
+  const int64_t j = idx - (int64_t)g * nb;
+  if (g >= G || g >= nt) return;
   const int qa = q_indptr[q];
   uint32_t* out = cur + (size_t)qa * (size_t)nb + (size_t)j * nt;
   const int64_t bound64 = j * bdocs;
   const uint32_t* cq = coarse ? coarse + (size_t)qa * (size_t)nbc : nullptr;
   const int64_t jc = j / ratio;
-  for (int u = 0; u < nt; ++u) {
+  for (int u = g; u < nt; u += G) {
     const uint32_t len = plan_len[qa + u];
     uint32_t lo = 0, hi = len;
     if (cq) {
@@ -221,6 +226,12 @@ bm25_plan_cursors_kernel(const int32_t* __restrict__ post_doc, const int32_t* __
     }
     out[u] = lo;
   }
+}
+// term groups for a table of nq * nb boundaries: enough threads to fill the GPU a few times over
+inline int bm25_plan_groups(int64_t nq, int64_t nb) {
+  const int64_t want = 2400000;
+  const int64_t g = (want + nq * nb - 1) / std::max<int64_t>(1, nq * nb);
+  return (int)std::min<int64_t>(8, std::max<int64_t>(1, g));
 }
 
 // sort buffer of the merge kernels (keys per query)

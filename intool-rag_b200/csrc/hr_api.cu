@@ -1468,17 +1468,19 @@ static int bm25_search_dev(hr_bm25* h, const int32_t* qi_dev, const int32_t* qt_
   {
     // coarse boundaries (every kBsCoarse slices) by a search over the whole list, then every slice boundary
     // inside its bracketing coarse pair
-    dim3 gridc((unsigned)nq, (unsigned)((nbc + 255) / 256));
+    const int gc = bm25_plan_groups(nq, nbc);
+    dim3 gridc((unsigned)nq, (unsigned)((nbc * gc + 255) / 256));
     bm25_plan_cursors_kernel<<<gridc, 256, 0, st>>>(h->post_doc, qi_dev, h->plan_nt.as<int>(),
                                                     h->plan_start.as<int64_t>(), h->plan_len.as<uint32_t>(), nbc,
                                                     (int64_t)slice_docs * kBsCoarse, nullptr, 0, 1,
-                                                    h->plan_coarse.as<uint32_t>());
+                                                    h->plan_coarse.as<uint32_t>(), gc);
     HR_LAUNCHED();
-    dim3 grid((unsigned)nq, (unsigned)((nsl + 1 + 255) / 256));
+    const int gf = bm25_plan_groups(nq, nsl + 1);
+    dim3 grid((unsigned)nq, (unsigned)(((nsl + 1) * gf + 255) / 256));
     bm25_plan_cursors_kernel<<<grid, 256, 0, st>>>(h->post_doc, qi_dev, h->plan_nt.as<int>(),
                                                    h->plan_start.as<int64_t>(), h->plan_len.as<uint32_t>(), nsl + 1,
                                                    (int64_t)slice_docs, h->plan_coarse.as<uint32_t>(), nbc, kBsCoarse,
-                                                   h->plan_cur.as<uint32_t>());
+                                                   h->plan_cur.as<uint32_t>(), gf);
     HR_LAUNCHED();
   }
   {
