@@ -34,21 +34,27 @@ fuse_kernel(const float* __restrict__ dD, const int64_t* __restrict__ dI, const 
   const int64_t* dIq = dI + (size_t)q * kc;
   const float* bSq = bS + (size_t)q * kc;
   const int64_t* bIq = bI + (size_t)q * kc;
+  // both id lists once into shared memory: every entry is looked up in the other list
+  __shared__ int64_t sdi[kFuseMaxKc], sbi[kFuseMaxKc];
   if (threadIdx.x == 0) s_valid = 0;
+  for (int e = threadIdx.x; e < kc; e += blockDim.x) {
+    sdi[e] = dIq[e];
+    sbi[e] = bIq[e];
+  }
   __syncthreads();
   float mx = 0.f;
   if (bmax) mx = bmax[q];
-  else if (bIq[0] >= 0) mx = bSq[0];  // lists are best-first
+  else if (sbi[0] >= 0) mx = bSq[0];  // lists are best-first
   const int n2 = 2 * kc;
   for (int e = threadIdx.x; e < n2; e += blockDim.x) {
     float f = 0.f;
     int64_t id = -1;
     if (e < kc) {
-      id = dIq[e];
+      id = sdi[e];
       if (id >= 0) {
         int sp = -1;
         for (int j = 0; j < kc; ++j)
-          if (bIq[j] == id) { sp = j; break; }
+          if (sbi[j] == id) { sp = j; break; }
         if (mode == 0) {
           float sim = (metric == 1) ? (1.0f - dDq[e] * 0.5f) : dDq[e];
           sim = fminf(1.0f, fmaxf(0.0f, sim));
@@ -61,11 +67,11 @@ fuse_kernel(const float* __restrict__ dD, const int64_t* __restrict__ dI, const 
       }
     } else {
       const int j = e - kc;
-      id = bIq[j];
+      id = sbi[j];
       if (id >= 0) {
         bool in_dense = false;
         for (int i = 0; i < kc; ++i)
-          if (dIq[i] == id) { in_dense = true; break; }
+          if (sdi[i] == id) { in_dense = true; break; }
         if (in_dense) id = -1;
         else if (mode == 0) f = (mx > 0.f) ? w_bm25 * (bSq[j] / mx) : 0.f;
         else f = 1.0f / (60.0f + (float)(j + 1));
