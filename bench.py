@@ -613,13 +613,13 @@ def run_b200(args):
             "kind::f16 (bf16 operands, fp32 accumulate in TMEM) over the bf16 rows; answers are exact fp32 after the re-score; "
             "peak = sustained cuBLAS bf16 (the kernel is timed inside a long step)")
     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture of this
-    # exact default workload (profiles/r1_scan_bm25_ncu_full.md); other workloads: not captured
+    # exact default workload (profiles/r2_scan_ncu.md, round 2; round 1: 20.83 GB); other workloads: not captured
     traffic = None
     if (world, args.rows, args.dim, args.nq, args.storage) == (1, 10_000_000, 1024, 1024, "f32+bf16"):
-        traffic = 20.791e9 + 0.039e9
+        traffic = 20.756e9 + 0.0375e9
     t_min_step = max(t_hbm, t_tensor) + touched * 8 / (pk["hbm_gbs"] * 1e9)
     roofline = {"kernel": kname, "bound": bound, "achieved": achieved, "peak": peak, "unit": runit,
-                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1_scan_bm25_ncu_full.md)",
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, profiles/r2_scan_ncu.md)",
                 "peak_source": pk["src"],
                 "kernel_ms": scan_ms, "share_of_step": scan_ms / ms_per_step,
                 "step_split_ms": {"dense_search_total": dense_in_step_ms, "scan_kernel": scan_ms,
