@@ -13,8 +13,6 @@ which = int(sys.argv[2]) if len(sys.argv) > 2 else len(idx) // 2
 a, b = idx[which], idx[which + 1] if which + 1 < len(idx) else len(data)
 tot = 0.0
 for k, v in data[a:b]:
-    if not k.startswith(("hr::", "void hr::")):
-        break
     print(f"{v:10.1f} us  {k}")
     tot += v
 print(f"{tot:10.1f} us  total")
